@@ -1,0 +1,68 @@
+// bec_rng.cuh -- in-kernel BEC erasure-pattern generator (device side).
+//
+// Replaces the reference channel  BEC.new_transmit  (/root/reference/channels.py:24-26:
+// `np.where(np.random.rand(n) < eps, 2, x)`) for the fused Monte-Carlo path: erasures are
+// i.i.d. Bernoulli(eps), strict '<', drawn from a counter-based generator keyed by
+// (seed, erasure point, 32-frame word index, variable) so that the pattern of frame f
+// does not depend on the GPU count, the launch geometry or the words-per-group choice.
+//
+//   key      = (seed_lo, seed_hi)                                  Philox4x32-10
+//   counter  = (variable, q_lo, q_hi, point << 8 | block)          q = frame >> 5
+//   block b yields the random words r[4b .. 4b+3]; r[j] carries bit (31-j) of the 32
+//   per-frame uniform integers U; frame (32q + bit) erases the variable iff U < T,
+//   T = ceil(eps * 2^32)  (computed on the host, see ldpc_b200.cu).
+//
+// The comparison runs MSB-first in bit-sliced form and stops as soon as every frame of
+// the word is decided, or all remaining bits of T are zero.
+#pragma once
+#include <stdint.h>
+
+namespace ldpc {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                              uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+struct BecParams {
+    uint32_t seed_lo, seed_hi;
+    uint32_t threshold;  // low 32 bits of T
+    uint32_t mode;       // 0: none erased (T == 0), 1: compare against threshold, 2: all erased (T == 2^32)
+};
+
+// 32 Bernoulli bits for (point, word q, variable var)
+__device__ __forceinline__ uint32_t bec_word(const BecParams& bp, uint32_t point, uint64_t q, uint32_t var) {
+    if (bp.mode != 1) return bp.mode == 2 ? 0xFFFFFFFFu : 0u;
+    const uint32_t t = bp.threshold;
+    uint32_t lt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int b = 0; b < 8; b++) {
+        uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
+        philox4x32_10(r0, r1, r2, r3, bp.seed_lo, bp.seed_hi);
+        const uint32_t r[4] = {r0, r1, r2, r3};
+        bool done = false;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (!done) {
+                const int j = 4 * b + s;
+                if ((t >> (31 - j)) & 1u) { lt |= eq & ~r[s]; eq &= r[s]; }
+                else                      { eq &= ~r[s]; }
+                // decided everywhere, or no set bit of T below this level
+                if (eq == 0u || j == 31 || (t << (j + 1)) == 0u) done = true;
+            }
+        }
+        if (done) break;
+    }
+    return lt;
+}
+
+}  // namespace ldpc

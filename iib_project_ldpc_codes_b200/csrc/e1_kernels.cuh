@@ -1,0 +1,518 @@
+// e1_kernels.cuh -- "E1": shared-memory-resident bit-sliced BEC flooding decoder (sm_100a).
+//
+// Hot path of /root/reference/message_passing.c:7-82 as driven by the frame loops of
+// /root/reference/parallel_simulator_expurgated.py:200-256 and :367-392, redesigned for B200:
+//
+//   * W = 32*WORDS frames share one machine word per Tanner-graph node ("frame group").
+//     The reference keeps ONE state value per variable (Mvc[i] in {0,1,2}, message_passing.c:54-60);
+//     its erasure plane obeys   x_i <- x_i AND (for every check c of i: c has >= 2 erased sockets)
+//     (SURVEY.md 7.1), so one flooding iteration is, per check, dc gathered words combined with
+//         two |= one & w ; one |= w
+//     and, per variable, dv gathered `two` words ANDed into x.  No tensor-core shaped work.
+//   * The graph (socket-major uint16 index arrays) is staged ONCE per CTA in shared memory;
+//     each team of warps owns a frame group whose state (x[n], two[m]) also lives in shared
+//     memory, so HBM is touched only by the final counter REDs (Monte-Carlo) or the
+//     pattern/result planes (batched decode).
+//   * Persistent CTAs (one per SM); teams pull frame groups from a global work counter.
+//   * Early termination / stall detection / erasure counts are warp REDUX (__reduce_or_sync,
+//     __reduce_add_sync) over the lanes of a team.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "bec_rng.cuh"
+
+namespace ldpc {
+
+constexpr int E1_MAX_THREADS = 512;
+
+template <int WORDS> struct VecT;
+template <> struct alignas(4)  VecT<1> { uint32_t a[1]; };
+template <> struct alignas(8)  VecT<2> { uint32_t a[2]; };
+template <> struct alignas(16) VecT<4> { uint32_t a[4]; };
+
+#define LDPC_FORW _Pragma("unroll") for (int w = 0; w < WORDS; w++)
+
+// raw device counter block per erasure point, all uint64:
+//   [0 .. cap]            per-iteration erasure sums (bin 0 = initial count), counted frames only
+//   [cap+1 .. cap+5]      block errors, bit errors, frames, counted frames, executed iterations
+//   [cap+6 .. 2cap+7]     tail difference array: tail[b] is added to every bin >= b (finalize kernel)
+//   [2cap+8]              physical frame-iterations (W * iterations the group actually ran)
+//   [2cap+9]              groups that needed the masked second pass (expurgation)
+__host__ __device__ inline int raw_stride(int cap) { return 2 * cap + 10; }
+
+struct E1Params {
+    // graph (global memory, socket-major uint16: idx[j * pad + node])
+    const uint16_t* c2v;
+    const uint16_t* v2c;
+    int n, m, dv, dc, n_pad, m_pad;
+    // geometry
+    int team_warps, teams;
+    // shared-memory byte offsets
+    uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride;
+    uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
+    // Monte-Carlo work
+    const BecParams* bec;  // [npoints]
+    int npoints, cap, expurgation;
+    unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
+    unsigned long long num_frames;      // frames per point
+    unsigned long long groups_per_point;
+    unsigned long long* counters;       // [npoints][raw_stride(cap)]
+    unsigned long long* work_counter;
+    // batched decode work (WORDS == 1)
+    const uint32_t* xin;   // [groups][n] erasure plane
+    const uint32_t* vin;   // [groups][n] value plane
+    uint32_t* xout;
+    uint32_t* vout;
+    int* errors;           // [frames][cap]
+    int* ret;              // [frames]
+};
+
+struct TeamCtx {
+    int tid;       // thread index inside the team
+    int nthr;      // threads in the team
+    int lane, warp;  // warp = warp index inside the team
+    int team_warps;
+    int bar_id;
+    uint32_t* scr;   // team scratch (shared)
+};
+
+__device__ __forceinline__ void team_sync(const TeamCtx& t) {
+    if (t.team_warps == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(t.bar_id), "r"(t.nthr) : "memory");
+}
+
+// OR-reduce NOR words and add-reduce one count across the team; result valid in every thread.
+// Contains one team_sync (which also orders the shared-memory state written before the call).
+template <int NOR>
+__device__ __forceinline__ void team_reduce(const TeamCtx& t, uint32_t (&ors)[NOR], uint32_t& sum) {
+#pragma unroll
+    for (int k = 0; k < NOR; k++) ors[k] = __reduce_or_sync(0xFFFFFFFFu, ors[k]);
+    sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+    if (t.team_warps == 1) { __syncwarp(); return; }
+    // scratch layout: [warp][NOR+1]; a single buffer is enough: the next write happens after the
+    // next check-phase barrier, which every warp reaches only after its reads below.
+    if (t.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NOR; k++) t.scr[t.warp * (NOR + 1) + k] = ors[k];
+        t.scr[t.warp * (NOR + 1) + NOR] = sum;
+    }
+    team_sync(t);
+    const bool have = t.lane < t.team_warps;
+#pragma unroll
+    for (int k = 0; k < NOR; k++) {
+        uint32_t v = have ? t.scr[t.lane * (NOR + 1) + k] : 0u;
+        ors[k] = __reduce_or_sync(0xFFFFFFFFu, v);
+    }
+    uint32_t s = have ? t.scr[t.lane * (NOR + 1) + NOR] : 0u;
+    sum = __reduce_add_sync(0xFFFFFFFFu, s);
+}
+
+// ---- check phase:  two[c] = [>= 2 erased sockets]  (message_passing.c:24-45 collapsed) ----
+template <int WORDS, int DV, int DC, bool VALUES>
+__device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t, const uint16_t* __restrict__ s_c2v,
+                                            const VecT<WORDS>* __restrict__ x, VecT<WORDS>* __restrict__ two,
+                                            const VecT<WORDS>* __restrict__ val, VecT<WORDS>* __restrict__ par) {
+    const int dc = DC ? DC : P.dc;
+    const int m = P.m, m_pad = P.m_pad;
+#pragma unroll 2
+    for (int c = t.tid; c < m; c += t.nthr) {
+        VecT<WORDS> one, tw, pr;
+        LDPC_FORW { one.a[w] = 0u; tw.a[w] = 0u; pr.a[w] = 0u; }
+#pragma unroll
+        for (int j = 0; j < dc; j++) {
+            const int v = s_c2v[j * m_pad + c];
+            const VecT<WORDS> xv = x[v];
+            LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
+            if (VALUES) {
+                const VecT<WORDS> vv = val[v];  // invariant: value bits are 0 where erased
+                LDPC_FORW pr.a[w] ^= vv.a[w];
+            }
+        }
+        two[c] = tw;
+        if (VALUES) par[c] = pr;
+    }
+}
+
+// ---- variable phase:  x_i &= AND_j two[v2c[i][j]]   (message_passing.c:52-65 collapsed) ----
+// VALUES: a variable resolved in this iteration takes the parity of the LAST listed check that
+// resolves it (message_passing.c:56-61 has no break: last writer wins).
+template <int WORDS, int DV, int DC, bool VALUES, bool MASKED>
+__device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, const uint16_t* __restrict__ s_v2c,
+                                          VecT<WORDS>* __restrict__ x, const VecT<WORDS>* __restrict__ two,
+                                          VecT<WORDS>* __restrict__ val, const VecT<WORDS>* __restrict__ par,
+                                          const uint32_t (&mask)[WORDS], uint32_t (&any)[WORDS],
+                                          uint32_t (&chg)[WORDS], uint32_t& cnt) {
+    const int dv = DV ? DV : P.dv;
+    const int n = P.n, n_pad = P.n_pad;
+    LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
+    cnt = 0u;
+#pragma unroll 2
+    for (int i = t.tid; i < n; i += t.nthr) {
+        const VecT<WORDS> xi = x[i];
+        VecT<WORDS> xn = xi, nv;
+        LDPC_FORW nv.a[w] = 0u;
+#pragma unroll
+        for (int j = 0; j < dv; j++) {
+            const int c = s_v2c[j * n_pad + i];
+            const VecT<WORDS> tw = two[c];
+            LDPC_FORW xn.a[w] &= tw.a[w];
+            if (VALUES) {
+                const VecT<WORDS> pr = par[c];
+                LDPC_FORW nv.a[w] = (nv.a[w] & tw.a[w]) | (pr.a[w] & ~tw.a[w]);
+            }
+        }
+        bool changed = false;
+        LDPC_FORW changed |= (xn.a[w] != xi.a[w]);
+        if (changed) {
+            x[i] = xn;
+            if (VALUES) {
+                VecT<WORDS> vi = val[i];
+                LDPC_FORW vi.a[w] |= nv.a[w] & xi.a[w] & ~xn.a[w];
+                val[i] = vi;
+            }
+        }
+        LDPC_FORW {
+            any[w] |= xn.a[w];
+            chg[w] |= xi.a[w] ^ xn.a[w];
+            cnt += __popc(MASKED ? (xn.a[w] & mask[w]) : xn.a[w]);
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add(unsigned long long* p, unsigned long long v) {
+    if (v) atomicAdd(p, v);
+}
+
+// Decode one frame group for the Monte-Carlo path.  MASKED pass: erasure sums restricted to `mask`.
+// Returns physical iterations executed; outputs the team-uniform masks / counts by reference.
+template <int WORDS, int DV, int DC, bool MASKED>
+__device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, const BecParams& bp, uint32_t point,
+                                        unsigned long long q0, const uint32_t (&valid)[WORDS],
+                                        const uint32_t (&mask)[WORDS], const uint16_t* s_c2v, const uint16_t* s_v2c,
+                                        VecT<WORDS>* x, VecT<WORDS>* two, uint32_t* hbuf, uint32_t (&any)[WORDS],
+                                        uint32_t& cnt, unsigned long long& exec_sum) {
+    // draw the erasure pattern (channels.py:24-26) straight into shared memory
+    uint32_t red[WORDS];
+    LDPC_FORW red[w] = 0u;
+    cnt = 0u;
+    for (int i = t.tid; i < P.n; i += t.nthr) {
+        VecT<WORDS> xi;
+        LDPC_FORW {
+            xi.a[w] = bec_word(bp, point, q0 + w, (uint32_t)i) & valid[w];
+            red[w] |= xi.a[w];
+            cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
+        }
+        x[i] = xi;
+    }
+    team_reduce<WORDS>(t, red, cnt);
+    LDPC_FORW any[w] = red[w];
+    if (t.tid == 0) hbuf[0] = cnt;
+
+    uint32_t running[WORDS];
+    LDPC_FORW running[w] = MASKED ? mask[w] : valid[w];
+    int it = 0;
+    exec_sum = 0;
+    for (; it < P.cap; it++) {
+        uint32_t r = 0u, pc = 0u;
+        LDPC_FORW { r |= running[w]; pc += __popc(running[w]); }
+        if (r == 0u) break;
+        exec_sum += pc;
+        check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
+        team_sync(t);
+        uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
+        var_phase<WORDS, DV, DC, false, MASKED>(P, t, s_v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
+        LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
+        team_reduce<2 * WORDS>(t, oc, cnt);
+        if (t.tid == 0) hbuf[it + 1] = cnt;
+        // message_passing.c:16-19: iterations 0 and 1 always run; from it>=2 a frame whose count did
+        // not change in the previous iteration is skipped forever.  :76-78: stop when nothing is erased.
+        LDPC_FORW {
+            any[w] = oc[w];
+            running[w] &= oc[w] & (it == 0 ? 0xFFFFFFFFu : oc[WORDS + w]);
+        }
+    }
+    return it;
+}
+
+template <int WORDS, int DV, int DC>
+__global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_mc_kernel(const __grid_constant__ E1Params P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
+    uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
+
+    // stage the graph once per CTA (16-byte vectors; arrays are padded to 16 bytes on the host)
+    {
+        const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
+        const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
+        const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
+        const uint4* g1 = reinterpret_cast<const uint4*>(P.v2c);
+        uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
+        uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+    }
+    __syncthreads();
+
+    TeamCtx t;
+    t.team_warps = P.team_warps;
+    t.nthr = P.team_warps * 32;
+    const int team = threadIdx.x / t.nthr;
+    t.tid = threadIdx.x - team * t.nthr;
+    t.lane = threadIdx.x & 31;
+    t.warp = t.tid >> 5;
+    t.bar_id = 1 + team;
+    unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
+    VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
+    VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
+    uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
+    t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
+    // scratch map: [0 .. 32*(2*WORDS+1))  reduce area ; then [work slot (2 words)] ; then rf[32*WORDS]
+    uint32_t* work_slot = t.scr + 32 * (2 * WORDS + 1);
+    uint32_t* rf = work_slot + 2;
+
+    const unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
+    const int W = 32 * WORDS;
+    const int stride = raw_stride(P.cap);
+
+    for (;;) {
+        // ---- fetch a work item (point, group) ----
+        unsigned long long item;
+        if (t.team_warps == 1) {
+            unsigned long long v = 0;
+            if (t.lane == 0) v = atomicAdd(P.work_counter, 1ull);
+            item = __shfl_sync(0xFFFFFFFFu, v, 0);
+        } else {
+            if (t.tid == 0) {
+                unsigned long long v = atomicAdd(P.work_counter, 1ull);
+                work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+            }
+            team_sync(t);
+            item = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+        }
+        if (item >= total) break;
+        const uint32_t point = (uint32_t)(item / P.groups_per_point);
+        const unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
+        const unsigned long long q0 = P.first_word + gi * WORDS;
+        const BecParams bp = P.bec[point];
+
+        uint32_t valid[WORDS];
+        LDPC_FORW {
+            const unsigned long long f0 = (gi * WORDS + w) * 32ull;  // first frame of this word, relative
+            valid[w] = f0 >= P.num_frames ? 0u
+                       : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+        }
+
+        uint32_t any[WORDS], cnt;
+        unsigned long long exec_sum;
+        int iters = mc_group<WORDS, DV, DC, false>(P, t, bp, point, q0, valid, valid, s_c2v, s_v2c, x, two, hbuf,
+                                                   any, cnt, exec_sum);
+        unsigned long long* C = P.counters + (size_t)point * stride;
+        unsigned long long phys = (unsigned long long)iters * W;
+        uint32_t nvalid = 0;
+        LDPC_FORW nvalid += __popc(valid[w]);
+
+        // ---- expurgation predicate: a frame counts iff its final residual > expurgation
+        //      (parallel_simulator_expurgated.py:238); denominators still count every frame (:258-260)
+        uint32_t K[WORDS];
+        LDPC_FORW K[w] = valid[w];
+        bool second = false;
+        if (P.expurgation >= 0) {
+            for (int f = t.tid; f < W; f += t.nthr) rf[f] = 0u;
+            team_sync(t);
+            LDPC_FORW {
+                uint32_t c = 0;
+                for (int i = t.warp; i < P.n; i += t.team_warps) c += (x[i].a[w] >> t.lane) & 1u;
+                if (c) atomicAdd(&rf[w * 32 + t.lane], c);
+            }
+            team_sync(t);
+            uint32_t kall = 0, kany = 0;
+            LDPC_FORW {
+                K[w] = __ballot_sync(0xFFFFFFFFu, (int)rf[w * 32 + t.lane] > P.expurgation) & valid[w];
+                kall |= K[w] ^ valid[w];
+                kany |= K[w];
+            }
+            team_sync(t);  // rf reads done before anything reuses scratch
+            if (kany == 0u) {
+                // nothing counted: only the denominators move
+                if (t.tid == 0) {
+                    red_add(C + P.cap + 3, nvalid);
+                    red_add(C + P.cap + 5, exec_sum);
+                    red_add(C + 2 * P.cap + 8, phys);
+                }
+                continue;
+            }
+            if (kall != 0u) {
+                // mixed group: re-decode with the erasure sums restricted to the counted frames
+                unsigned long long e2;
+                iters = mc_group<WORDS, DV, DC, true>(P, t, bp, point, q0, valid, K, s_c2v, s_v2c, x, two, hbuf,
+                                                      any, cnt, e2);
+                phys += (unsigned long long)iters * W;
+                second = true;
+            }
+        }
+        // ---- flush the group's statistics (parallel_simulator_expurgated.py:239-243) ----
+        team_sync(t);  // hbuf writes by thread 0 visible to the team
+        for (int b = t.tid; b <= iters; b += t.nthr) red_add(C + b, hbuf[b]);
+        if (t.tid == 0) {
+            if (iters < P.cap) red_add(C + P.cap + 6 + iters + 1, cnt);  // bins iters+1 .. cap keep the residual
+            uint32_t blk = 0, nk = 0;
+            LDPC_FORW { blk += __popc(any[w] & K[w]); nk += __popc(K[w]); }
+            red_add(C + P.cap + 1, blk);
+            red_add(C + P.cap + 2, cnt);
+            red_add(C + P.cap + 3, nvalid);
+            red_add(C + P.cap + 4, nk);
+            red_add(C + P.cap + 5, exec_sum);
+            red_add(C + 2 * P.cap + 8, phys);
+            if (second) red_add(C + 2 * P.cap + 9, 1ull);
+        }
+        team_sync(t);  // hbuf is rewritten by the next group
+    }
+}
+
+// tail[b] is added to every bin >= b:  bins after a group's last physical iteration keep its residual
+__global__ void e1_finalize_kernel(unsigned long long* counters, int npoints, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npoints) return;
+    unsigned long long* C = counters + (size_t)p * raw_stride(cap);
+    unsigned long long run = 0;
+    for (int b = 0; b <= cap; b++) {
+        run += C[cap + 6 + b];
+        C[cap + 6 + b] = 0;
+        C[b] += run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched decode (parity API and the single-frame drop-in): W = 32, value plane optional, per-frame
+// errors[] / return value exactly as message_passing.c:7-82 produces them for zeroed `errors`.
+// ------------------------------------------------------------------------------------------------
+template <int DV, int DC, bool VALUES>
+__global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_decode_kernel(const __grid_constant__ E1Params P) {
+    constexpr int WORDS = 1;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
+    uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
+    {
+        const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
+        const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
+        const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
+        const uint4* g1 = reinterpret_cast<const uint4*>(P.v2c);
+        uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
+        uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+    }
+    __syncthreads();
+
+    TeamCtx t;
+    t.team_warps = P.team_warps;
+    t.nthr = P.team_warps * 32;
+    const int team = threadIdx.x / t.nthr;
+    t.tid = threadIdx.x - team * t.nthr;
+    t.lane = threadIdx.x & 31;
+    t.warp = t.tid >> 5;
+    t.bar_id = 1 + team;
+    unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
+    VecT<1>* x = reinterpret_cast<VecT<1>*>(base + P.sm_x);
+    VecT<1>* two = reinterpret_cast<VecT<1>*>(base + P.sm_t);
+    VecT<1>* val = reinterpret_cast<VecT<1>*>(base + P.sm_v);
+    VecT<1>* par = reinterpret_cast<VecT<1>*>(base + P.sm_p);
+    t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
+    uint32_t* rf = t.scr + 32 * (2 * WORDS + 1) + 2;
+
+    const unsigned long long groups = P.groups_per_point;
+    for (unsigned long long gi = (unsigned long long)blockIdx.x * P.teams + team; gi < groups;
+         gi += (unsigned long long)gridDim.x * P.teams) {
+        const unsigned long long f0 = gi * 32ull;
+        const uint32_t valid = P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u);
+        const uint32_t* gx = P.xin + (size_t)gi * P.n;
+        const uint32_t* gv = P.vin + (size_t)gi * P.n;
+        for (int i = t.tid; i < P.n; i += t.nthr) {
+            const uint32_t xi = gx[i] & valid;
+            x[i].a[0] = xi;
+            if (VALUES) val[i].a[0] = gv[i] & ~xi & valid;
+        }
+        team_sync(t);
+
+        const unsigned long long frame = f0 + t.lane;
+        const bool mine = (valid >> t.lane) & 1u;     // every warp of the team mirrors the 32 frames in its lanes
+        int my_ret = P.cap;
+        uint32_t running = valid;
+        uint32_t my_count = 0;
+        int it = 0;
+        for (; it < P.cap; it++) {
+            if (running == 0u) break;
+            check_phase<1, DV, DC, VALUES>(P, t, s_c2v, x, two, val, par);
+            if (t.tid < 32) rf[t.tid] = 0u;
+            team_sync(t);
+            uint32_t a2[1], c2[1], cnt, mask1[1] = {0xFFFFFFFFu};
+            var_phase<1, DV, DC, VALUES, false>(P, t, s_v2c, x, two, val, par, mask1, a2, c2, cnt);
+            uint32_t oc[2] = {a2[0], c2[0]};
+            team_reduce<2>(t, oc, cnt);
+            // per-frame erasure count after this iteration (message_passing.c:70-75)
+            {
+                uint32_t c = 0;
+                for (int i = t.warp; i < P.n; i += t.team_warps) c += (x[i].a[0] >> t.lane) & 1u;
+                if (c) atomicAdd(&rf[t.lane], c);
+            }
+            team_sync(t);
+            my_count = rf[t.lane];
+            if (mine && t.warp == 0) P.errors[frame * (unsigned long long)P.cap + it] = (int)my_count;
+            if (((running >> t.lane) & 1u) && !((oc[0] >> t.lane) & 1u) && my_ret == P.cap) my_ret = it;  // :76-78
+            running &= oc[0] & (it == 0 ? 0xFFFFFFFFu : oc[1]);  // :16-19
+            team_sync(t);  // rf is zeroed again in the next iteration
+        }
+        // skipped iterations copy the previous count (:16-19); after success the caller's zeros stay
+        if (mine && t.warp == 0) {
+            for (int j = it; j < P.cap; j++) P.errors[frame * (unsigned long long)P.cap + j] = (int)my_count;
+            P.ret[frame] = my_ret;
+        }
+        uint32_t* ox = P.xout + (size_t)gi * P.n;
+        uint32_t* ov = P.vout + (size_t)gi * P.n;
+        for (int i = t.tid; i < P.n; i += t.nthr) { ox[i] = x[i].a[0]; ov[i] = VALUES ? val[i].a[0] : 0u; }
+        team_sync(t);
+    }
+}
+
+// Mvc int8 [frames][n] in {0,1,2}  ->  bit planes [groups][n] (bit b of word = frame 32g+b)
+__global__ void pack_planes_kernel(const int8_t* __restrict__ mvc, uint32_t* __restrict__ xpl, uint32_t* __restrict__ vpl,
+                                   unsigned long long frames, int n) {
+    const unsigned long long g = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t xw = 0, vw = 0;
+    for (int b = 0; b < 32; b++) {
+        const unsigned long long f = g * 32ull + b;
+        if (f < frames) {
+            const int8_t s = mvc[f * (unsigned long long)n + i];
+            xw |= (uint32_t)(s == 2) << b;
+            vw |= (uint32_t)(s == 1) << b;
+        }
+    }
+    xpl[g * (unsigned long long)n + i] = xw;
+    vpl[g * (unsigned long long)n + i] = vw;
+}
+
+__global__ void unpack_planes_kernel(int8_t* __restrict__ mvc, const uint32_t* __restrict__ xpl,
+                                     const uint32_t* __restrict__ vpl, unsigned long long frames, int n) {
+    const unsigned long long g = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t xw = xpl[g * (unsigned long long)n + i], vw = vpl[g * (unsigned long long)n + i];
+    for (int b = 0; b < 32; b++) {
+        const unsigned long long f = g * 32ull + b;
+        if (f < frames) mvc[f * (unsigned long long)n + i] = ((xw >> b) & 1u) ? 2 : (int8_t)((vw >> b) & 1u);
+    }
+}
+
+// erasure patterns of the in-kernel generator, as bit planes [groups][n] (used by the parity tests
+// to feed the reference C decoder exactly what the fused Monte-Carlo kernel decoded)
+__global__ void draw_planes_kernel(uint32_t* __restrict__ xpl, BecParams bp, uint32_t point,
+                                   unsigned long long first_word, unsigned long long words, int n) {
+    const unsigned long long g = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || g >= words) return;
+    xpl[g * (unsigned long long)n + i] = bec_word(bp, point, first_word + g, (uint32_t)i);
+}
+
+}  // namespace ldpc

@@ -1,0 +1,565 @@
+// ldpc_b200.cu -- C ABI (include/ldpc_b200.h) over the sm_100a kernels.  GPU-only: every entry point
+// fails loudly (negative status + ldpc_b200_last_error()) when it cannot run on the device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <stdarg.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+
+#include "../../include/ldpc_b200.h"
+#include "e1_kernels.cuh"
+
+using namespace ldpc;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(LDPC_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+extern "C" const char* ldpc_b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int ldpc_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int ldpc_b200_counters_len(int iterations) { return iterations + 6; }
+
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+struct E1Config {
+    int words = 0, teams = 0, team_warps = 0;
+    bool values = false;
+    uint32_t smem = 0;
+    uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
+};
+
+struct ldpc_b200_graph {
+    int n = 0, k = 0, m = 0, dv = 0, dc = 0, device = 0;
+    int n_pad = 0, m_pad = 0;
+    std::vector<int> v2c, c2v;     // host copies, reference layouts
+    uint16_t* d_c2v16 = nullptr;   // socket-major [dc][m_pad]
+    uint16_t* d_v2c16 = nullptr;   // socket-major [dv][n_pad]
+    int sm_count = 0, smem_optin = 0;
+    // workspace
+    unsigned long long* d_work = nullptr;
+    unsigned long long* d_raw = nullptr; size_t raw_cap = 0;
+    BecParams* d_bec = nullptr; int bec_cap = 0;
+    unsigned long long* d_out = nullptr; size_t out_cap = 0;  // for mc_run
+    // tuning overrides
+    int tune_words = 0, tune_teams = 0, tune_team_warps = 0;
+    // statistics of launches since last read
+    unsigned long long* d_stats = nullptr;  // [2]: phys frame-iterations, second-pass groups
+    ldpc_b200_mc_stats last = {};
+    // kernel timing ring
+    static constexpr int RING = 256;
+    cudaEvent_t ev0[RING], ev1[RING];
+    int ev_count = 0;
+    bool ev_init = false;
+};
+
+static int tuning_env(const char* name) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : 0;
+}
+
+// Shared-memory plan for E1.  Returns false if even one W=32 team does not fit.
+static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode, E1Config& cfg) {
+    const uint32_t limit = (uint32_t)g->smem_optin;
+    const uint32_t graph_bytes = align_up((uint32_t)g->dc * g->m_pad * 2, 16) + align_up((uint32_t)g->dv * g->n_pad * 2, 16);
+    if (g->n > 65535) return false;
+    auto team_bytes = [&](int words, E1Config& c) {
+        uint32_t off = 0;
+        c.sm_x = off; off += align_up((uint32_t)g->n * 4 * words, 16);
+        c.sm_t = off; off += align_up((uint32_t)g->m * 4 * words, 16);
+        c.sm_v = off; if (values) off += align_up((uint32_t)g->n * 4 * words, 16);
+        c.sm_p = off; if (values) off += align_up((uint32_t)g->m * 4 * words, 16);
+        c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
+        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words) * 4, 16);
+        return off;
+    };
+    int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
+    int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
+    int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
+    const int max_warps = E1_MAX_THREADS / 32;
+    const int cand[3] = {4, 2, 1};
+    for (int ci = 0; ci < 3; ci++) {
+        int words = cand[ci];
+        if (decode && words != 1) continue;
+        if (want_words && words != want_words) continue;
+        E1Config c;
+        uint32_t tb = team_bytes(words, c);
+        if (graph_bytes + tb > limit) continue;
+        int fit = (int)((limit - graph_bytes) / tb);
+        const int min_teams = want_words ? 1 : (words == 4 ? 4 : (words == 2 ? 2 : 1));
+        if (fit < min_teams) continue;
+        int teams = std::min(fit, max_warps);
+        if (want_teams) teams = std::min(want_teams, fit);
+        int tw = want_tw ? want_tw : std::max(1, max_warps / teams);
+        if (tw > 1 && teams > 15) teams = 15;  // named barriers 1..15
+        while (teams * tw > max_warps && tw > 1) tw--;
+        if (teams * tw > max_warps) teams = max_warps / tw;
+        if (teams < 1) continue;
+        c.words = words; c.teams = teams; c.team_warps = tw; c.values = values;
+        c.sm_c2v = 0;
+        c.sm_v2c = align_up((uint32_t)g->dc * g->m_pad * 2, 16);
+        c.sm_team0 = graph_bytes;
+        c.sm_team_stride = tb;
+        c.smem = graph_bytes + tb * teams;
+        cfg = c;
+        return true;
+    }
+    return false;
+}
+
+static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1Params& P) {
+    memset(&P, 0, sizeof P);
+    P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
+    P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
+    P.team_warps = c.team_warps; P.teams = c.teams;
+    P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
+    P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
+    P.cap = cap;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int k, int dv, int dc, int device,
+                                      ldpc_b200_graph** out) {
+    if (!out) return fail(LDPC_B200_EINVAL, "graph_create: out is NULL");
+    *out = nullptr;
+    if (!v2c || !c2v) return fail(LDPC_B200_EINVAL, "graph_create: NULL lookup");
+    if (n <= 0 || dv <= 0 || dc <= 0 || k < 0 || k >= n) return fail(LDPC_B200_EINVAL, "graph_create: bad sizes n=%d k=%d dv=%d dc=%d", n, k, dv, dc);
+    const int m = n - k;
+    if ((long long)m * dc != (long long)n * dv)
+        return fail(LDPC_B200_EINVAL, "graph_create: (n-k)*dc != n*dv (n=%d k=%d dv=%d dc=%d)", n, k, dv, dc);
+    if (dv > 64 || dc > 64) return fail(LDPC_B200_EUNSUPPORTED, "graph_create: degree > 64");
+    const long long E = (long long)n * dv;
+    for (long long e = 0; e < E; e++) {
+        if (v2c[e] < 0 || v2c[e] >= m) return fail(LDPC_B200_EINVAL, "graph_create: variable_to_check_list[%lld]=%d out of range", e, v2c[e]);
+        if (c2v[e] < 0 || c2v[e] >= n) return fail(LDPC_B200_EINVAL, "graph_create: check_to_variable_list[%lld]=%d out of range", e, c2v[e]);
+    }
+    // every check a variable lists must hold that variable in one of its sockets (the kernels use
+    // "check c resolves i" <=> "c has exactly one erased socket"; message_passing.c:58 searches the socket)
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < dv; j++) {
+            const int c = v2c[(long long)i * dv + j];
+            bool found = false;
+            for (int l = 0; l < dc; l++) found |= (c2v[(long long)c * dc + l] == i);
+            if (!found) return fail(LDPC_B200_EINVAL, "graph_create: variable %d lists check %d which has no socket for it", i, c);
+        }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LDPC_B200_ECUDA, "graph_create: device %d not present (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+
+    ldpc_b200_graph* g = new ldpc_b200_graph();
+    g->n = n; g->k = k; g->m = m; g->dv = dv; g->dc = dc; g->device = device;
+    g->n_pad = (int)align_up((uint32_t)n, 8); g->m_pad = (int)align_up((uint32_t)m, 8);
+    g->v2c.assign(v2c, v2c + E); g->c2v.assign(c2v, c2v + E);
+    cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&g->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (n <= 65535) {
+        std::vector<uint16_t> h_c((size_t)dc * g->m_pad, 0), h_v((size_t)dv * g->n_pad, 0);
+        for (int c = 0; c < m; c++) for (int j = 0; j < dc; j++) h_c[(size_t)j * g->m_pad + c] = (uint16_t)c2v[(size_t)c * dc + j];
+        for (int i = 0; i < n; i++) for (int j = 0; j < dv; j++) h_v[(size_t)j * g->n_pad + i] = (uint16_t)v2c[(size_t)i * dv + j];
+        const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16);
+        cudaError_t e = cudaMalloc(&g->d_c2v16, bc);
+        if (e == cudaSuccess) e = cudaMalloc(&g->d_v2c16, bv);
+        if (e == cudaSuccess) e = cudaMemset(g->d_c2v16, 0, bc);
+        if (e == cudaSuccess) e = cudaMemset(g->d_v2c16, 0, bv);
+        if (e == cudaSuccess) e = cudaMemcpy(g->d_c2v16, h_c.data(), h_c.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(g->d_v2c16, h_v.data(), h_v.size() * 2, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ldpc_b200_graph_destroy(g); return fail(LDPC_B200_ECUDA, "graph_create: %s", cudaGetErrorString(e)); }
+    }
+    {
+        cudaError_t e = cudaMalloc(&g->d_work, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&g->d_stats, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, 2 * sizeof(unsigned long long));
+        if (e != cudaSuccess) { ldpc_b200_graph_destroy(g); return fail(LDPC_B200_ECUDA, "graph_create: %s", cudaGetErrorString(e)); }
+    }
+    *out = g;
+    return LDPC_B200_OK;
+}
+
+extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
+    cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
+    if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
+    delete g;
+}
+
+extern "C" int ldpc_b200_set_tuning(ldpc_b200_graph* g, int words, int teams, int team_warps) {
+    if (!g) return fail(LDPC_B200_EINVAL, "set_tuning: NULL graph");
+    if (words != 0 && words != 1 && words != 2 && words != 4) return fail(LDPC_B200_EINVAL, "set_tuning: words must be 0,1,2,4");
+    g->tune_words = words; g->tune_teams = teams; g->tune_team_warps = team_warps;
+    return LDPC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static BecParams make_bec(double eps, uint64_t seed) {
+    BecParams bp;
+    bp.seed_lo = (uint32_t)seed; bp.seed_hi = (uint32_t)(seed >> 32);
+    // u < eps for u = U / 2^32, U uniform 32-bit  <=>  U < T, T = ceil(eps * 2^32) (channels.py:26 is strict)
+    if (!(eps > 0.0)) { bp.mode = 0; bp.threshold = 0; }
+    else if (eps >= 1.0) { bp.mode = 2; bp.threshold = 0; }
+    else {
+        double t = ceil(eps * 4294967296.0);
+        if (t >= 4294967296.0) { bp.mode = 2; bp.threshold = 0; }
+        else { bp.mode = 1; bp.threshold = (uint32_t)t; }
+    }
+    return bp;
+}
+
+template <int WORDS>
+static cudaError_t launch_mc_words(const E1Params& P, int grid, int block, uint32_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, block, smem, st>>>(P);
+        return cudaGetLastError();
+    };
+    if (P.dv == 3 && P.dc == 6) return go(e1_mc_kernel<WORDS, 3, 6>);
+    if (P.dv == 4 && P.dc == 8) return go(e1_mc_kernel<WORDS, 4, 8>);
+    return go(e1_mc_kernel<WORDS, 0, 0>);
+}
+
+__global__ void mc_compact_kernel(const unsigned long long* raw, unsigned long long* out, unsigned long long* stats,
+                                  int npoints, int cap) {
+    // raw has been finalized; add the public counter block into `out`, perf counters into `stats`
+    const int p = blockIdx.x;
+    const unsigned long long* C = raw + (size_t)p * raw_stride(cap);
+    for (int b = threadIdx.x; b < cap + 6; b += blockDim.x) out[(size_t)p * (cap + 6) + b] += C[b];
+    if (threadIdx.x == 0) {
+        atomicAdd(stats + 0, C[2 * cap + 8]);
+        atomicAdd(stats + 1, C[2 * cap + 9]);
+    }
+}
+
+static int ensure_events(ldpc_b200_graph* g) {
+    if (g->ev_init) return LDPC_B200_OK;
+    for (int i = 0; i < ldpc_b200_graph::RING; i++) {
+        CUDA_TRY(cudaEventCreate(&g->ev0[i]));
+        CUDA_TRY(cudaEventCreate(&g->ev1[i]));
+    }
+    g->ev_init = true;
+    return LDPC_B200_OK;
+}
+
+extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+                                   uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                                   uint64_t* d_counters, void* stream) {
+    if (!g || !eps || !d_counters) return fail(LDPC_B200_EINVAL, "mc_launch: NULL argument");
+    if (npoints <= 0 || npoints >= (1 << 24)) return fail(LDPC_B200_EINVAL, "mc_launch: npoints out of range");
+    if (iterations < 0 || iterations > 65535) return fail(LDPC_B200_EINVAL, "mc_launch: iterations out of range");
+    if (first_frame % 128 != 0) return fail(LDPC_B200_EINVAL, "mc_launch: first_frame must be a multiple of 128");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(g->device));
+    if (num_frames == 0) return LDPC_B200_OK;
+
+    E1Config cfg;
+    if (!plan_e1(g, iterations, false, false, cfg))
+        return fail(LDPC_B200_EUNSUPPORTED, "mc_launch: graph (n=%d dv=%d dc=%d) does not fit the shared-memory engine and the streamed engine is not built", g->n, g->dv, g->dc);
+
+    const int cap = iterations;
+    const size_t raw_words = (size_t)npoints * raw_stride(cap);
+    if (g->raw_cap < raw_words) {
+        cudaFree(g->d_raw); g->d_raw = nullptr; g->raw_cap = 0;
+        CUDA_TRY(cudaMalloc(&g->d_raw, raw_words * 8));
+        g->raw_cap = raw_words;
+    }
+    if (g->bec_cap < npoints) {
+        cudaFree(g->d_bec); g->d_bec = nullptr; g->bec_cap = 0;
+        CUDA_TRY(cudaMalloc(&g->d_bec, sizeof(BecParams) * (size_t)npoints));
+        g->bec_cap = npoints;
+    }
+    std::vector<BecParams> hb(npoints);
+    for (int p = 0; p < npoints; p++) hb[p] = make_bec(eps[p], seed);
+    CUDA_TRY(cudaMemcpyAsync(g->d_bec, hb.data(), sizeof(BecParams) * (size_t)npoints, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // hb is a stack-lifetime pageable buffer
+    CUDA_TRY(cudaMemsetAsync(g->d_raw, 0, raw_words * 8, st));
+    CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
+
+    E1Params P;
+    fill_params(g, cfg, cap, P);
+    const unsigned long long W = 32ull * cfg.words;
+    P.bec = g->d_bec; P.npoints = npoints; P.expurgation = expurgation;
+    P.first_word = first_frame / 32; P.num_frames = num_frames;
+    P.groups_per_point = (num_frames + W - 1) / W;
+    P.counters = g->d_raw; P.work_counter = g->d_work;
+    const unsigned long long items = P.groups_per_point * (unsigned long long)npoints;
+    const unsigned long long ctas_needed = (items + cfg.teams - 1) / cfg.teams;
+    const int grid = (int)std::min<unsigned long long>((unsigned long long)g->sm_count, ctas_needed);
+    const int block = cfg.teams * cfg.team_warps * 32;
+
+    int rc = ensure_events(g);
+    if (rc) return rc;
+    const int slot = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
+    if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));
+    cudaError_t e;
+    if (cfg.words == 4) e = launch_mc_words<4>(P, grid, block, cfg.smem, st);
+    else if (cfg.words == 2) e = launch_mc_words<2>(P, grid, block, cfg.smem, st);
+    else e = launch_mc_words<1>(P, grid, block, cfg.smem, st);
+    if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "mc_launch: kernel launch failed: %s", cudaGetErrorString(e));
+    if (slot >= 0) { CUDA_TRY(cudaEventRecord(g->ev1[slot], st)); g->ev_count++; }
+    e1_finalize_kernel<<<(npoints + 127) / 128, 128, 0, st>>>(g->d_raw, npoints, cap);
+    mc_compact_kernel<<<npoints, 128, 0, st>>>(g->d_raw, (unsigned long long*)d_counters, g->d_stats, npoints, cap);
+    CUDA_TRY(cudaGetLastError());
+
+    g->last.engine = 1; g->last.words = cfg.words; g->last.teams = cfg.teams; g->last.team_warps = cfg.team_warps;
+    g->last.grid = grid; g->last.smem_bytes = (int)cfg.smem;
+    return LDPC_B200_OK;
+}
+
+extern "C" int ldpc_b200_mc_stats_read(ldpc_b200_graph* g, ldpc_b200_mc_stats* stats) {
+    if (!g || !stats) return fail(LDPC_B200_EINVAL, "mc_stats_read: NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpy(h, g->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(g->d_stats, 0, sizeof h));
+    *stats = g->last;
+    stats->phys_frame_iterations = h[0];
+    stats->second_pass_groups = h[1];
+    return LDPC_B200_OK;
+}
+
+extern "C" int ldpc_b200_kernel_times(ldpc_b200_graph* g, float* ms, int max) {
+    if (!g || !ms) return fail(LDPC_B200_EINVAL, "kernel_times: NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    int n = std::min(g->ev_count, max);
+    for (int i = 0; i < n; i++) {
+        CUDA_TRY(cudaEventSynchronize(g->ev1[i]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[i], g->ev0[i], g->ev1[i]));
+    }
+    g->ev_count = 0;
+    return n;
+}
+
+extern "C" int ldpc_b200_mc_run(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+                                uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                                uint64_t* counters, ldpc_b200_mc_stats* stats) {
+    if (!g || !eps || !counters) return fail(LDPC_B200_EINVAL, "mc_run: NULL argument");
+    if (npoints <= 0) return fail(LDPC_B200_EINVAL, "mc_run: npoints <= 0");
+    if (iterations < 0) return fail(LDPC_B200_EINVAL, "mc_run: iterations < 0");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t words = (size_t)npoints * (iterations + 6);
+    if (g->out_cap < words) {
+        cudaFree(g->d_out); g->d_out = nullptr; g->out_cap = 0;
+        CUDA_TRY(cudaMalloc(&g->d_out, words * 8));
+        g->out_cap = words;
+    }
+    CUDA_TRY(cudaMemsetAsync(g->d_out, 0, words * 8, 0));
+    int rc = ldpc_b200_mc_launch(g, eps, npoints, seed, first_frame, num_frames, iterations, expurgation,
+                                 (uint64_t*)g->d_out, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(counters, g->d_out, words * 8, cudaMemcpyDeviceToHost));
+    if (stats) return ldpc_b200_mc_stats_read(g, stats);
+    return LDPC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool VALUES>
+static cudaError_t launch_decode(const E1Params& P, int grid, int block, uint32_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, block, smem, st>>>(P);
+        return cudaGetLastError();
+    };
+    if (P.dv == 3 && P.dc == 6) return go(e1_decode_kernel<3, 6, VALUES>);
+    if (P.dv == 4 && P.dc == 8) return go(e1_decode_kernel<4, 8, VALUES>);
+    return go(e1_decode_kernel<0, 0, VALUES>);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
+                                      int* errors, int* ret) {
+    if (!g || !Mvc || !ret || (!errors && iterations > 0)) return fail(LDPC_B200_EINVAL, "decode_batch: NULL argument");
+    if (iterations < 0) return fail(LDPC_B200_EINVAL, "decode_batch: iterations < 0");
+    if (frames == 0) return LDPC_B200_OK;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t total = (size_t)frames * g->n;
+    bool values = false;
+    for (size_t i = 0; i < total; i++) {
+        const int8_t s = Mvc[i];
+        if (s < 0 || s > 2) return fail(LDPC_B200_EINVAL, "decode_batch: symbol %d at frame %zu position %zu is outside {0,1,2}", (int)s, i / g->n, i % g->n);
+        values |= (s == 1);
+    }
+    E1Config cfg;
+    if (!plan_e1(g, iterations, values, true, cfg))
+        return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: graph (n=%d dv=%d dc=%d, value plane %s) does not fit the shared-memory engine and the streamed engine is not built",
+                    g->n, g->dv, g->dc, values ? "on" : "off");
+    const uint64_t groups = (frames + 31) / 32;
+    DevBuf d_mvc, d_x, d_v, d_err, d_ret;
+    CUDA_TRY(d_mvc.alloc(total));
+    CUDA_TRY(d_x.alloc(groups * g->n * 4));
+    CUDA_TRY(d_v.alloc(groups * g->n * 4));
+    CUDA_TRY(d_err.alloc((size_t)frames * iterations * 4));
+    CUDA_TRY(d_ret.alloc((size_t)frames * 4));
+    CUDA_TRY(cudaMemcpy(d_mvc.p, Mvc, total, cudaMemcpyHostToDevice));
+    dim3 pgrid((g->n + 127) / 128, (unsigned)groups);
+    if (groups > 65535) return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: more than 65535*32 frames per call");
+    pack_planes_kernel<<<pgrid, 128>>>((const int8_t*)d_mvc.p, (uint32_t*)d_x.p, (uint32_t*)d_v.p, frames, g->n);
+    CUDA_TRY(cudaGetLastError());
+
+    E1Params P;
+    fill_params(g, cfg, iterations, P);
+    P.num_frames = frames; P.groups_per_point = groups;
+    P.xin = (const uint32_t*)d_x.p; P.vin = (const uint32_t*)d_v.p;
+    P.xout = (uint32_t*)d_x.p; P.vout = (uint32_t*)d_v.p;
+    P.errors = (int*)d_err.p; P.ret = (int*)d_ret.p;
+    const int grid = (int)std::min<uint64_t>((uint64_t)g->sm_count, (groups + cfg.teams - 1) / cfg.teams);
+    const int block = cfg.teams * cfg.team_warps * 32;
+    cudaError_t e = values ? launch_decode<true>(P, grid, block, cfg.smem, 0) : launch_decode<false>(P, grid, block, cfg.smem, 0);
+    if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "decode_batch: kernel launch failed: %s", cudaGetErrorString(e));
+    unpack_planes_kernel<<<pgrid, 128>>>((int8_t*)d_mvc.p, (const uint32_t*)d_x.p, (const uint32_t*)d_v.p, frames, g->n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(Mvc, d_mvc.p, total, cudaMemcpyDeviceToHost));
+    if (iterations > 0) CUDA_TRY(cudaMemcpy(errors, d_err.p, (size_t)frames * iterations * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ret, d_ret.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
+    return LDPC_B200_OK;
+}
+
+extern "C" int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32_t point,
+                                       uint64_t first_frame, uint64_t frames, int8_t* out) {
+    if (!out || n <= 0) return fail(LDPC_B200_EINVAL, "draw_patterns: bad argument");
+    if (first_frame % 32 != 0) return fail(LDPC_B200_EINVAL, "draw_patterns: first_frame must be a multiple of 32");
+    if (frames == 0) return LDPC_B200_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    const uint64_t words = (frames + 31) / 32;
+    if (words > 65535) return fail(LDPC_B200_EUNSUPPORTED, "draw_patterns: more than 65535*32 frames per call");
+    DevBuf d_x, d_v, d_m;
+    CUDA_TRY(d_x.alloc(words * n * 4));
+    CUDA_TRY(d_v.alloc(words * n * 4));
+    CUDA_TRY(d_m.alloc(frames * n));
+    CUDA_TRY(cudaMemset(d_v.p, 0, words * n * 4));
+    dim3 grid((n + 127) / 128, (unsigned)words);
+    draw_planes_kernel<<<grid, 128>>>((uint32_t*)d_x.p, make_bec(eps, seed), point, first_frame / 32, words, n);
+    unpack_planes_kernel<<<grid, 128>>>((int8_t*)d_m.p, (const uint32_t*)d_x.p, (const uint32_t*)d_v.p, frames, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, d_m.p, frames * n, cudaMemcpyDeviceToHost));
+    return LDPC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// message_passing.c:7 drop-in.  Device copies of the graph are cached by content hash because the
+// reference passes the same lookups for every frame in fixed-code mode (parallel_simulator.py:360).
+static std::mutex g_cache_mutex;
+struct CacheEntry { ldpc_b200_graph* g; uint64_t hash; };
+static std::unordered_map<uint64_t, ldpc_b200_graph*> g_cache;
+
+static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+extern "C" int message_passing(int* Mvc, int iterations, int* variable_to_check_list, int* check_to_variable_list,
+                               int* errors, int n, int k, int dv, int dc) {
+    if (!Mvc || !variable_to_check_list || !check_to_variable_list || (!errors && iterations > 0))
+        return fail(LDPC_B200_EINVAL, "message_passing: NULL argument");
+    if (iterations <= 0) return 0;  // message_passing.c:15,81: loop does not run, returns it == 0
+    const size_t E = (size_t)n * dv;
+    uint64_t h = 1469598103934665603ull;
+    const int dims[4] = {n, k, dv, dc};
+    h = fnv1a(dims, sizeof dims, h);
+    h = fnv1a(variable_to_check_list, E * sizeof(int), h);
+    h = fnv1a(check_to_variable_list, E * sizeof(int), h);
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    ldpc_b200_graph* g = nullptr;
+    auto itc = g_cache.find(h);
+    if (itc != g_cache.end()) {
+        g = itc->second;
+        if (g->n != n || g->k != k || g->dv != dv || g->dc != dc ||
+            memcmp(g->v2c.data(), variable_to_check_list, E * sizeof(int)) != 0 ||
+            memcmp(g->c2v.data(), check_to_variable_list, E * sizeof(int)) != 0)
+            g = nullptr;  // hash collision: fall through to an uncached handle
+    }
+    bool cached = g != nullptr;
+    if (!g) {
+        const char* dev_s = getenv("LDPC_B200_DEVICE");
+        int rc = ldpc_b200_graph_create(variable_to_check_list, check_to_variable_list, n, k, dv, dc,
+                                        dev_s ? atoi(dev_s) : 0, &g);
+        if (rc) return rc;
+        if (itc == g_cache.end()) {
+            if (g_cache.size() >= 64) {  // bound the cache
+                for (auto& kv : g_cache) ldpc_b200_graph_destroy(kv.second);
+                g_cache.clear();
+            }
+            g_cache[h] = g;
+            cached = true;
+        }
+    }
+    struct Guard { ldpc_b200_graph* g; bool keep; ~Guard() { if (!keep) ldpc_b200_graph_destroy(g); } } guard{g, cached};
+
+    std::vector<int8_t> frame(n);
+    for (int i = 0; i < n; i++) {
+        if (Mvc[i] < 0 || Mvc[i] > 2) return fail(LDPC_B200_EINVAL, "message_passing: Mvc[%d]=%d outside {0,1,2}", i, Mvc[i]);
+        frame[i] = (int8_t)Mvc[i];
+    }
+    std::vector<int8_t> input = frame;
+    std::vector<int> cnt(iterations);
+    int ret = 0;
+    int rc = ldpc_b200_decode_batch(g, frame.data(), 1, iterations, cnt.data(), &ret);
+    if (rc) return rc;
+
+    bool prefilled = false;
+    for (int it = 0; it < iterations; it++) prefilled |= (errors[it] != 0);
+    if (!prefilled) {
+        for (int it = 0; it < iterations; it++) errors[it] = cnt[it];
+        for (int i = 0; i < n; i++) Mvc[i] = frame[i];
+        return ret;
+    }
+    // Caller did not zero errors[] (the reference accumulates with +=, message_passing.c:73, and its
+    // stall test :16 compares the ACCUMULATED values).  cnt[j] is the erased count after j+1 executed
+    // flooding iterations; replay the reference's control flow over it.
+    int executed = 0, it = 0;
+    for (; it < iterations; it++) {
+        if (it > 1 && errors[it - 1] == errors[it - 2]) { errors[it] = errors[it - 1]; continue; }
+        const int c = cnt[executed];
+        executed++;
+        errors[it] += c;
+        if (c == 0) break;
+    }
+    // state after `executed` iterations
+    if (executed < iterations) {
+        frame = input;
+        std::vector<int> tmp(std::max(executed, 1));
+        int r2 = 0;
+        if (executed > 0) {
+            rc = ldpc_b200_decode_batch(g, frame.data(), 1, executed, tmp.data(), &r2);
+            if (rc) return rc;
+        }
+    }
+    for (int i = 0; i < n; i++) Mvc[i] = frame[i];
+    return it;
+}

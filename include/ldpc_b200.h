@@ -1,0 +1,125 @@
+/*
+ * ldpc_b200.h -- C ABI of libldpc_b200.so: the B200 (sm_100a) implementation of the BEC
+ * message-passing Monte-Carlo hot path of roryhighnam/iib_project_ldpc_codes.
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types in any signature.  All entry points are
+ * GPU-only: there is no CPU fallback.  A call that cannot run on the GPU returns a negative status
+ * and ldpc_b200_last_error() says why.
+ *
+ * Reference interfaces replaced (file:line relative to the reference repository):
+ *   message_passing            message_passing.c:7        (called from parallel_simulator.py:162-164,
+ *                                                          parallel_simulator_expurgated.py:162-164)
+ *   generate_random_code       random_code_generator.c:21 (called from parallel_simulator_expurgated.py:223,
+ *                                                          peeling_decoder.py:42)
+ *   ldpc_b200_decode_batch     a loop of message_passing.c:7 calls over frames, i.e. the body of
+ *                              regular_LDPC_code.message_pass_decode (parallel_simulator.py:131-166)
+ *   ldpc_b200_mc_run / _launch the frame loops run_simulation (parallel_simulator_expurgated.py:200-256)
+ *                              and run_simulation_fixed_ldpc (:367-392) including the channel draw
+ *                              (channels.py:24-26) and the expurgation predicate (:238)
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_OK            0
+#define LDPC_B200_EINVAL      (-1)  /* bad argument / malformed graph / symbol outside {0,1,2} */
+#define LDPC_B200_ECUDA       (-2)  /* CUDA runtime failure (no device, launch error, out of memory) */
+#define LDPC_B200_EUNSUPPORTED (-3) /* configuration not supported by this build */
+
+typedef struct ldpc_b200_graph ldpc_b200_graph;
+
+typedef struct ldpc_b200_mc_stats {
+    uint64_t phys_frame_iterations; /* frame-iterations the kernel physically ran (lock-step groups)       */
+    uint64_t second_pass_groups;    /* frame groups re-decoded for the expurgation filter                  */
+    int32_t engine;                 /* 1 = shared-memory resident (E1), 2 = HBM/L2 streamed (E2)          */
+    int32_t words;                  /* 32-bit words per node and frame group (frames per group = 32*words)*/
+    int32_t teams;                  /* frame groups resident per CTA                                       */
+    int32_t team_warps;             /* warps cooperating on one frame group                                */
+    int32_t grid;                   /* CTAs launched                                                       */
+    int32_t smem_bytes;             /* dynamic shared memory per CTA                                       */
+} ldpc_b200_mc_stats;
+
+/* ---- reference drop-ins ------------------------------------------------------------------- */
+
+/* message_passing.c:7 -- identical arguments, in-place outputs and return value.
+ * Mvc[n] in {0,1,2} (2 = erased) is decoded in place; errors[it] += erased count after iteration it
+ * (caller zeroes, as parallel_simulator.py:147 does); returns the iteration index at which no erasure
+ * was left, else `iterations`.  Runs on the GPU (device 0 unless LDPC_B200_DEVICE is set); device
+ * copies of the graph are cached by content.  Returns a negative LDPC_B200_E* on failure (no valid
+ * reference result is negative). */
+int message_passing(int *Mvc, int iterations, int *variable_to_check_list, int *check_to_variable_list,
+                    int *errors, int n, int k, int dv, int dc);
+
+/* random_code_generator.c:21 -- same arguments and outputs (host code; the graph is built on the CPU
+ * in the reference too).  Differences, all supersets: parity_check may be NULL (the dense (n-k) x n
+ * matrix is impossible at n = 10^6), variable_lookup is built sparsely, and retries are iterative. */
+int generate_random_code(int n, int dv, int dc, int *variable_lookup, int *check_lookup, int *sequence,
+                         bool *parity_check, int iterations, bool first_run, int seed);
+
+/* ---- library ------------------------------------------------------------------------------ */
+
+const char *ldpc_b200_last_error(void);
+int ldpc_b200_device_count(void);
+
+/* Seeded, sparse generator with the (variable_lookup, check_lookup) contract of
+ * random_code_generator.c:34-36,53-64: socket permutation + rejection of graphs with a repeated
+ * variable in a check; check_lookup unsorted within a check, variable_lookup in ascending check order.
+ * mode 0: pure rejection (the reference's distribution); mode 1: repair repeated variables by socket
+ * swaps (needed for (4,8) and large n where rejection takes > 10^4 shuffles).  Returns 1 on success. */
+int ldpc_b200_generate_graph(int n, int dv, int dc, uint64_t seed, int mode, int *variable_lookup, int *check_lookup);
+
+/* Upload a Tanner graph: variable_to_check_list [n][dv], check_to_variable_list [n-k][dc], int32,
+ * the layouts of message_passing.c:7.  k must equal n - n*dv/dc. */
+int ldpc_b200_graph_create(const int *variable_to_check_list, const int *check_to_variable_list,
+                           int n, int k, int dv, int dc, int device, ldpc_b200_graph **out);
+void ldpc_b200_graph_destroy(ldpc_b200_graph *g);
+
+/* Counter block per erasure point (uint64, additive over disjoint frame ranges and over GPUs):
+ *   [0 .. iterations]  sum over COUNTED frames of [initial_count, errors[0 .. iterations-1]]
+ *   [iterations+1]     block errors      [iterations+2]  bit errors
+ *   [iterations+3]     frames (all)      [iterations+4]  counted frames (errors[-1] > expurgation)
+ *   [iterations+5]     executed iterations summed over all frames (edge updates = this * n * dv) */
+int ldpc_b200_counters_len(int iterations);
+
+/* Fused Monte-Carlo over frames [first_frame, first_frame + num_frames) of every erasure point:
+ * draw erasures on the device, decode, accumulate.  first_frame must be a multiple of 128.
+ * expurgation < 0 counts every frame (parallel_simulator.py:227-231).
+ * counters: HOST buffer [npoints][ldpc_b200_counters_len(iterations)], overwritten. stats may be NULL. */
+int ldpc_b200_mc_run(ldpc_b200_graph *g, const double *eps, int npoints, uint64_t seed,
+                     uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                     uint64_t *counters, ldpc_b200_mc_stats *stats);
+
+/* Same, asynchronous on `stream` (a cudaStream_t, or NULL), ADDING into the DEVICE buffer d_counters
+ * of the same shape.  Nothing is copied to the host. */
+int ldpc_b200_mc_launch(ldpc_b200_graph *g, const double *eps, int npoints, uint64_t seed,
+                        uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                        uint64_t *d_counters, void *stream);
+/* statistics of the launches since the last call (call after synchronising the stream) */
+int ldpc_b200_mc_stats_read(ldpc_b200_graph *g, ldpc_b200_mc_stats *stats);
+/* device durations (ms, CUDA events on the launch stream) of the decode kernels launched since the
+ * last call; returns how many were written (<= max) */
+int ldpc_b200_kernel_times(ldpc_b200_graph *g, float *ms, int max);
+
+/* Batched decode: Mvc HOST [frames][n] int8 in {0,1,2}, decoded in place; errors HOST
+ * [frames][iterations] receives what message_passing.c leaves in a zeroed errors[]; ret [frames]. */
+int ldpc_b200_decode_batch(ldpc_b200_graph *g, int8_t *Mvc, uint64_t frames, int iterations,
+                           int *errors, int *ret);
+
+/* Erasure patterns of the in-kernel generator for frames [first_frame, first_frame+frames), first_frame
+ * a multiple of 32: out HOST [frames][n] int8 in {0,2}.  Computed on the GPU with the kernel's code. */
+int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32_t point,
+                            uint64_t first_frame, uint64_t frames, int8_t *out);
+
+/* Tuning overrides (0 = automatic): words in {1,2,4}, teams per CTA, warps per team. */
+int ldpc_b200_set_tuning(ldpc_b200_graph *g, int words, int teams, int team_warps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
