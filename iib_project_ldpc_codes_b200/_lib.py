@@ -41,7 +41,7 @@ EXPORTS = [
     "message_passing", "generate_random_code", "ldpc_b200_last_error", "ldpc_b200_device_count",
     "ldpc_b200_generate_graph", "ldpc_b200_graph_create", "ldpc_b200_graph_destroy", "ldpc_b200_counters_len",
     "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
-    "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning",
+    "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning", "ldpc_b200_smem_probe",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def load() -> ct.CDLL:
     lib.ldpc_b200_draw_patterns.restype = ct.c_int
     lib.ldpc_b200_draw_patterns.argtypes = [ct.c_int, ct.c_int, ct.c_double, ct.c_uint64, ct.c_uint32, ct.c_uint64,
                                             ct.c_uint64, P_I8]
+    lib.ldpc_b200_smem_probe.restype = ct.c_int
+    lib.ldpc_b200_smem_probe.argtypes = [ct.c_int, P_F64]
     lib.ldpc_b200_set_tuning.restype = ct.c_int
     lib.ldpc_b200_set_tuning.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int]
     _lib = lib

@@ -174,3 +174,11 @@ def message_passing(Mvc, iterations, variable_to_check_list, check_to_variable_l
         assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
     return check(lib.message_passing(ptr(Mvc, P_I32), iterations, ptr(variable_to_check_list, P_I32),
                                      ptr(check_to_variable_list, P_I32), ptr(errors, P_I32), n, k, dv, dc))
+
+
+def smem_bandwidth_gbs(device=0):
+    """Measured whole-GPU shared-memory read bandwidth (GB/s), the E1 roofline denominator."""
+    lib = _lib.load()
+    v = ct.c_double(0.0)
+    check(lib.ldpc_b200_smem_probe(device, ct.byref(v)))
+    return v.value

@@ -471,6 +471,56 @@ extern "C" int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t s
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shared-memory bandwidth probe: the roofline denominator for the shared-memory-resident engine is
+// measured on the box (conflict-free LDS.128 streams from every SM), not taken from a data sheet.
+__global__ void __launch_bounds__(1024, 1) smem_probe_kernel(uint4* sink, int iters) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint4* s = reinterpret_cast<uint4*>(sm);
+    const int words = 4096;  // 64 KB
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s[i] = make_uint4(i, i * 3, i * 5, i * 7);
+    __syncthreads();
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    int idx = threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint4 v = s[(idx + k * 256) & (words - 1)];
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        idx = (idx + 1024) & (words - 1);
+    }
+    if (acc.x == 0x12345678u && acc.y == 1u) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+extern "C" int ldpc_b200_smem_probe(int device, double* gbytes_per_s) {
+    if (!gbytes_per_s) return fail(LDPC_B200_EINVAL, "smem_probe: NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DevBuf sink;
+    CUDA_TRY(sink.alloc((size_t)sms * 1024 * sizeof(uint4)));
+    CUDA_TRY(cudaFuncSetAttribute(smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 4000;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        smem_probe_kernel<<<sms, 1024, 65536>>>((uint4*)sink.p, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double bytes = (double)sms * 1024.0 * iters * 16.0 * 16.0;
+        if (rep >= 1) best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gbytes_per_s = best;
+    return LDPC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // message_passing.c:7 drop-in.  Device copies of the graph are cached by content hash because the
 // reference passes the same lookups for every frame in fixed-code mode (parallel_simulator.py:360).
 static std::mutex g_cache_mutex;

@@ -116,6 +116,10 @@ int ldpc_b200_decode_batch(ldpc_b200_graph *g, int8_t *Mvc, uint64_t frames, int
 int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32_t point,
                             uint64_t first_frame, uint64_t frames, int8_t *out);
 
+/* Measured shared-memory read bandwidth of the whole GPU (conflict-free 128-bit loads from every SM),
+ * in GB/s: the roofline denominator of the shared-memory-resident engine. */
+int ldpc_b200_smem_probe(int device, double *gbytes_per_s);
+
 /* Tuning overrides (0 = automatic): words in {1,2,4}, teams per CTA, warps per team. */
 int ldpc_b200_set_tuning(ldpc_b200_graph *g, int words, int teams, int team_warps);
 
