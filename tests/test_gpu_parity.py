@@ -240,3 +240,58 @@ def test_mc_statistical_anchor_density_evolution(L, g1000):
     for got, want in zip(avg[:4], [0.4, 0.313756, 0.267938, 0.236467]):
         assert abs(got - want) < 2e-3
     assert 0.05 < r.block_error_rate < 0.15      # FER ~ 0.085-0.087 (code dependent)
+
+
+# ---- committed golden vectors (outputs of the unmodified reference C, tests/golden/make_golden.py) ----
+def test_golden_single_frame_through_dropin_symbol(L):
+    from golden_util import mp_cases
+    for c in mp_cases():
+        M = c["inp"].astype(np.int32)
+        err = c["prefill"].astype(np.int32).copy()
+        ret = L.message_passing(M, c["its"], c["v2c"].copy(), c["c2v"].copy(), err if c["its"] else np.zeros(1, np.int32),
+                                c["n"], c["k"], c["dv"], c["dc"])
+        assert ret == c["ret"] and np.array_equal(M, c["out"])
+        if c["its"]:
+            assert np.array_equal(err, c["errors"])
+
+
+def test_golden_monte_carlo_counters(L):
+    from golden_util import mc_cases
+    for c in mc_cases():
+        g = L.Graph(c["v2c"].reshape(c["n"], c["dv"]), c["c2v"].reshape(-1, c["dc"]))
+        for words in (0, 1, 2, 4):
+            g.set_tuning(words, 0, 0)
+            got = g.mc_run(c["eps"], c["seed"], c["frames"], c["its"], expurgation=c["expurgation"],
+                           first_frame=c["first"])
+            assert np.array_equal(got, c["counters"]), (c["n"], c["its"], c["expurgation"], words)
+
+
+def test_sharded_equals_whole(L, g1000):
+    """The multi-GPU split (dist.shard_frames + one sum) reproduces the single-range counters bit for bit."""
+    from iib_project_ldpc_codes_b200.dist import shard_frames
+    eps, its, seed, total = [0.40, 0.43], 200, 4242, 5000
+    whole = g1000.mc_run(eps, seed, total, its)
+    for world in (2, 4, 8):
+        acc = np.zeros_like(whole)
+        for r in range(world):
+            lo, cnt = shard_frames(total, r, world)
+            if cnt:
+                acc += g1000.mc_run(eps, seed, cnt, its, first_frame=lo)
+        assert np.array_equal(acc, whole)
+
+
+def test_full_size_properties_c2(L):
+    """BASELINE config 2 at a larger frame count: size-independent invariants of the counter block."""
+    vl, cl = L.generate_graph(10000, 3, 6, seed=1, mode=1)
+    g = L.Graph(vl, cl)
+    its, frames = 200, 200000
+    c = g.mc_run([0.38, 0.43], 12345, frames, its)
+    for row, eps in zip(c, (0.38, 0.43)):
+        hist = row[: its + 1].astype(np.int64)
+        assert (np.diff(hist) <= 0).all()                       # erasure counts never grow
+        assert row[its + 3] == frames == row[its + 4]
+        assert row[its + 2] == hist[-1]                         # bit errors = final residual sum
+        assert abs(hist[0] / (frames * 10000) - eps) < 1e-4     # channel rate
+        assert frames <= row[its + 5] <= frames * its           # executed iterations
+    assert c[0][its + 1] == 0                                   # eps=0.38 << threshold: every frame decodes
+    assert c[1][its + 1] == frames                              # eps=0.43 > threshold 0.4294: none does
