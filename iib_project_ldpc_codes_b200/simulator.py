@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference drivers for the message-passing path, over the GPU library.
+
+Same names, argument meaning and outputs as the reference (file:line relative to the reference repo):
+
+  BEC                         channels.py:4-26                           (host numpy; the fused path draws in-kernel)
+  regular_LDPC_code           parallel_simulator_expurgated.py:44-53
+    .message_pass_decode      parallel_simulator_expurgated.py:131-167   -> (int32 sequence, errors[max_its+1])
+  run_simulation              parallel_simulator_expurgated.py:169-285   (ensemble mode, expurgation filter)
+  run_simulation_fixed_ldpc   parallel_simulator_expurgated.py:287-414   (fixed code, .npy cache, no filter)
+  write_message_passing_file  parallel_simulator.py:26-32                (CSV rows + filename schema)
+  main(argv)                  parallel_simulator_expurgated.py:418-459   eps num_tests iterations n dv dc mode <seed|filenumber> [expurgation]
+
+Out of scope here: the ML decoder (`optimal_decode`, modes 1/2/4/5 raise NotImplementedError).
+
+Differences that follow from batching (documented, not hidden):
+  * the 200-block-error stop rule (:200, :367) is evaluated between batches of frames, so a run can
+    overshoot the 200th failure by at most one batch; `stop_rule_batch` sets the granularity;
+  * ensemble mode draws one fresh graph per FRAME GROUP (`frames_per_graph`, default 128) instead of one
+    per frame: the expectation of every statistic over the ensemble is unchanged (frames are exchangeable),
+    frames sharing a graph are correlated through the code only;
+  * erasures come from the counter-based in-kernel generator keyed by (seed, eps point, frame), so runs ARE
+    reproducible (the reference ignores its seed, random_code_generator.c:22-25, and uses unseeded numpy).
+"""
+from __future__ import annotations
+
+import csv
+import os
+import sys
+import time
+from datetime import datetime
+
+import numpy as np
+
+from . import api
+
+base_directory = os.environ.get("LDPC_B200_BASE_DIRECTORY", os.getcwd() + os.sep)
+
+
+def _sim_dir():
+    d = os.path.join(base_directory, "report_data", "simulation_data")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def write_message_passing_file(filename, errors, message_passing_block_error, message_passing_bit_error):
+    """parallel_simulator.py:26-32: iterations+1 rows of average erased fraction, then two labelled rows."""
+    with open(os.path.join(_sim_dir(), filename), "w", newline="") as csvfile:
+        writer = csv.writer(csvfile)
+        for error_at_iteration in errors:
+            writer.writerow([error_at_iteration])
+        writer.writerow(["Message passing block-wise error", message_passing_block_error])
+        writer.writerow(["Message passing bit-wise error", message_passing_bit_error])
+
+
+class BEC:
+    """channels.py:4-26."""
+
+    def __init__(self, erasure_prob):
+        self.erasure_prob = erasure_prob
+
+    def transmit(self, input_binary):
+        input_binary = np.where(input_binary == 0, -1, input_binary)
+        random_vector = np.random.rand(len(input_binary))
+        return np.where(random_vector < self.erasure_prob, 0, input_binary)
+
+    def new_transmit(self, input_binary):
+        random_vector = np.random.rand(len(input_binary))
+        return np.where(random_vector < self.erasure_prob, 2, input_binary)
+
+
+class regular_LDPC_code:
+    """parallel_simulator_expurgated.py:44-53; the dense parity_check is carried but never needed by the
+    message-passing path when the lookups are passed (and may be None here)."""
+
+    def __init__(self, parity_check, n, k, dv, dc):
+        self.parity_check = parity_check
+        self.n, self.k, self.dv, self.dc = n, k, dv, dc
+        self.rate = self.k / self.n
+
+    def _lookups_from_H(self):
+        H = np.asarray(self.parity_check)
+        check_lookup = [list(np.nonzero(row == 1)[0]) for row in H]
+        variable_lookup = [list(np.nonzero(col == 1)[0]) for col in H.T]
+        return check_lookup, variable_lookup
+
+    def message_pass_decode(self, binary_sequence, max_its, check_lookup=None, variable_lookup=None):
+        if check_lookup is None or variable_lookup is None:
+            cl, vl = self._lookups_from_H()
+            check_lookup = cl if check_lookup is None else check_lookup
+            variable_lookup = vl if variable_lookup is None else variable_lookup
+        check_lookup = np.array(check_lookup, dtype="int32").flatten()
+        variable_lookup = np.array(variable_lookup, dtype="int32").flatten()
+        errors = np.zeros(max(max_its, 1), dtype="int32")
+        binary_sequence = np.array(binary_sequence, dtype="int32")
+        initial_error_count = int(np.count_nonzero(binary_sequence == 2))
+        api.message_passing(binary_sequence, max_its, variable_lookup, check_lookup, errors, self.n, self.k, self.dv, self.dc)
+        errors = np.insert(errors[:max_its], 0, initial_error_count)
+        return binary_sequence, errors
+
+    def optimal_decode(self, binary_sequence):
+        raise NotImplementedError("ML decoding (ml_decoder.c + galois) is outside the accelerated hot path")
+
+
+def _filename(prefix, eps, n, k, dv, dc, iterations, num):
+    return (prefix + "_BEC=" + str(eps) + "_n=" + str(n) + "_k=" + str(k) + "_dv=" + str(dv) + "_dc=" + str(dc) +
+            "_it=" + str(iterations) + "_num=" + str(num) + "_time=" + datetime.now().strftime("%d-%m-%Y-%H-%M-%S") + ".csv")
+
+
+def _finish(prefix, eps, n, k, dv, dc, iterations, counters, write_csv):
+    its = iterations
+    frames = int(counters[its + 3])
+    average_errors = counters[: its + 1].astype(np.float64) / (n * max(frames, 1))
+    block = int(counters[its + 1]) / max(frames, 1)
+    bit = int(counters[its + 2]) / (max(frames, 1) * n)
+    filename = _filename(prefix, eps, n, k, dv, dc, iterations, frames)
+    if write_csv:
+        write_message_passing_file(filename, average_errors, block, bit)
+    return {"filename": filename, "average_errors": average_errors, "block_error": block, "bit_error": bit,
+            "num_tests": frames, "block_errors": int(counters[its + 1]), "bit_errors": int(counters[its + 2]),
+            "counters": counters}
+
+
+def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=None, stop_rule_batch=None,
+                              wall_clock_limit=42000):
+    """Fixed-code Monte-Carlo (parallel_simulator_expurgated.py:287-414)."""
+    eps = parameter_set["BEC"]
+    num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
+    n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]
+    if parameter_set.get("optimal"):
+        raise NotImplementedError("ML decoding is outside the accelerated hot path")
+    filenumber = parameter_set["filenumber"]
+    k = int(n * (dc - dv) / dc)
+    start = time.time()
+    pdir = os.path.join(base_directory, "parity_checks")
+    os.makedirs(pdir, exist_ok=True)
+    tag = str(filenumber) + "_n_" + str(n) + "_dv_" + str(dv) + "_dc_" + str(dc) + ".npy"
+    check_path = os.path.join(pdir, "check_code_no_" + tag)
+    var_path = os.path.join(pdir, "variable_code_no_" + tag)
+    if os.path.exists(check_path) and os.path.exists(var_path):          # :303-319 (the dense code_no_* file is not needed)
+        check_lookup = np.load(check_path)
+        variable_lookup = np.load(var_path)
+    else:                                                                 # :322-348
+        variable_lookup, check_lookup = api.generate_graph(n, dv, dc, seed=int(filenumber), mode=1)
+        np.save(check_path, check_lookup.ravel())
+        np.save(var_path, variable_lookup.ravel())
+    g = api.Graph(np.asarray(variable_lookup).reshape(n, dv), np.asarray(check_lookup).reshape(n - k, dc), device=device)
+    seed = int(filenumber) if run_seed is None else run_seed
+    total = np.zeros(iterations + 6, dtype=np.uint64)
+    done = 0
+    batch = stop_rule_batch or max(4096, min(num_tests, 1 << 22))
+    batch = (batch + 127) // 128 * 128
+    # :367  while block_error<200 and i<num_tests and elapsed < 42000
+    while int(total[iterations + 1]) < 200 and done < num_tests and time.time() - start < wall_clock_limit:
+        cnt = min(batch, num_tests - done)
+        total += g.mc_run([eps], seed, cnt, iterations, expurgation=-1, first_frame=done)[0]
+        done += cnt
+    g.close()
+    return _finish("regular_code_code_number=" + str(filenumber), eps, n, k, dv, dc, iterations, total, write_csv)
+
+
+def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=64,
+                   wall_clock_limit=43000):
+    """Ensemble Monte-Carlo (parallel_simulator_expurgated.py:169-285): a fresh random graph per frame group."""
+    eps = parameter_set["BEC"]
+    num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
+    n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]
+    if parameter_set.get("optimal"):
+        raise NotImplementedError("ML decoding is outside the accelerated hot path")
+    seed = int(parameter_set["seed"])
+    expurgation = int(parameter_set.get("expurgation", -1))
+    k = int(n * (dc - dv) / dc)
+    start = time.time()
+    frames_per_graph = (frames_per_graph + 127) // 128 * 128
+    total = np.zeros(iterations + 6, dtype=np.uint64)
+    done, gi = 0, 0
+    while int(total[iterations + 1]) < 200 and done < num_tests and time.time() - start < wall_clock_limit:   # :200
+        for _ in range(stop_rule_graphs):
+            if done >= num_tests:
+                break
+            vl, cl = api.generate_graph(n, dv, dc, seed=seed * 1000003 + gi, mode=1)
+            g = api.Graph(vl, cl, device=device)
+            cnt = min(frames_per_graph, num_tests - done)
+            total += g.mc_run([eps], seed, cnt, iterations, expurgation=expurgation, first_frame=gi * frames_per_graph)[0]
+            g.close()
+            done += cnt
+            gi += 1
+    return _finish("regular_code_expurgated=" + str(expurgation), eps, n, k, dv, dc, iterations, total, write_csv)
+
+
+def main(argv=None):
+    """parallel_simulator_expurgated.py:418-459 positional CLI."""
+    argv = sys.argv if argv is None else argv
+    erasure_prob = float(argv[1]); num_tests = int(argv[2]); iterations = int(argv[3])
+    n = int(argv[4]); dv = int(argv[5]); dc = int(argv[6]); mode = int(argv[7])
+    expurgation = int(argv[9]) if len(argv) > 9 else -1
+    if mode == 0:
+        d = {"BEC": erasure_prob, "expurgation": expurgation, "num_tests": num_tests, "iterations": iterations, "n": n,
+             "dv": dv, "dc": dc, "optimal": False, "message_passing": True, "seed": int(argv[8])}
+        return run_simulation(d)
+    if mode == 3:
+        d = {"BEC": erasure_prob, "num_tests": num_tests, "iterations": iterations, "n": n, "dv": dv, "dc": dc,
+             "optimal": False, "message_passing": True, "filenumber": int(argv[8])}
+        return run_simulation_fixed_ldpc(d)
+    if mode in (1, 2, 4, 5):
+        raise NotImplementedError("modes 1,2,4,5 use the ML decoder, which is outside the accelerated hot path")
+    raise ValueError("Mode value must be in the range 0-5")
+
+
+if __name__ == "__main__":
+    r = main()
+    print(r["filename"], "block", r["block_error"], "bit", r["bit_error"], "num", r["num_tests"])

@@ -1,0 +1,99 @@
+"""GPU tests of the host-side mirror of the reference drivers (iib_project_ldpc_codes_b200/simulator.py)."""
+import csv
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def S(built, tmp_path):
+    import iib_project_ldpc_codes_b200 as L
+    if L._lib.load().ldpc_b200_device_count() < 1:
+        pytest.fail("no CUDA device")
+    from iib_project_ldpc_codes_b200 import simulator as S
+    S.base_directory = str(tmp_path) + os.sep
+    return S
+
+
+def test_message_pass_decode_matches_reference_wrapper_semantics(S, oracle):
+    """(int32 sequence, errors with the initial count prepended) as parallel_simulator_expurgated.py:131-167."""
+    import iib_project_ldpc_codes_b200 as L
+    n, dv, dc = 512, 3, 6
+    vl, cl = L.generate_graph(n, dv, dc, seed=5)
+    code = S.regular_LDPC_code(None, n, n // 2, dv, dc)
+    np.random.seed(3)
+    ch = S.BEC(0.41)
+    for _ in range(10):
+        y = ch.new_transmit(np.zeros(n))
+        dec, errors = code.message_pass_decode(y, 50, cl, vl)
+        M, err, ret = oracle.single_frame("ref" if oracle.have_ref() else "orc", y.astype(np.int32), 50, vl, cl, n, n // 2, dv, dc)
+        assert dec.dtype == np.int32 and np.array_equal(dec, M)
+        assert len(errors) == 51 and errors[0] == np.count_nonzero(y == 2) and np.array_equal(errors[1:], err)
+
+
+def test_message_pass_decode_from_dense_parity_check(S):
+    import iib_project_ldpc_codes_b200 as L
+    n, dv, dc = 60, 3, 6
+    vl, cl = L.generate_graph(n, dv, dc, seed=8)
+    H = np.zeros((n // 2, n), dtype=np.int8)
+    for c in range(n // 2):
+        H[c, cl[c]] = 1
+    code = S.regular_LDPC_code(H, n, n // 2, dv, dc)
+    y = np.zeros(n); y[[1, 7, 30]] = 2
+    dec, errors = code.message_pass_decode(y, 20)
+    assert errors[0] == 3 and (dec == 0).all() and errors[-1] == 0
+
+
+def test_run_simulation_fixed_ldpc_counters_csv_and_cache(S, oracle):
+    p = {"BEC": 0.42, "num_tests": 3000, "iterations": 60, "n": 504, "dv": 3, "dc": 6, "optimal": False,
+         "message_passing": True, "filenumber": 7}
+    r = S.run_simulation_fixed_ldpc(p, stop_rule_batch=1024, run_seed=11)
+    pdir = os.path.join(S.base_directory, "parity_checks")
+    cl = np.load(os.path.join(pdir, "check_code_no_7_n_504_dv_3_dc_6.npy")).reshape(252, 6)
+    vl = np.load(os.path.join(pdir, "variable_code_no_7_n_504_dv_3_dc_6.npy")).reshape(504, 3)
+    frames = r["num_tests"]
+    assert frames % 1024 == 0 or frames == 3000
+    want = oracle.best().mc_run(vl, cl, 504, 252, 3, 6, [0.42], 11, 0, frames, 60, -1, nthreads=8)[0]
+    assert np.array_equal(r["counters"], want)
+    assert r["block_errors"] >= 200 or frames == 3000          # stop rule, batch granularity
+    # CSV: iterations+1 rows, then the two labelled rows (parallel_simulator.py:26-32); filename schema
+    path = os.path.join(S.base_directory, "report_data", "simulation_data", r["filename"])
+    rows = list(csv.reader(open(path)))
+    assert len(rows) == 63
+    assert rows[61][0] == "Message passing block-wise error" and rows[62][0] == "Message passing bit-wise error"
+    assert abs(float(rows[0][0]) - 0.42) < 0.01
+    assert float(rows[61][1]) == r["block_error"]
+    for key in ("regular_code_code_number=7", "_BEC=0.42", "_n=504", "_k=252", "_dv=3", "_dc=6", "_it=60", f"_num={frames}"):
+        assert key in r["filename"]
+    # second run reuses the cached code files
+    r2 = S.run_simulation_fixed_ldpc(p, stop_rule_batch=1024, run_seed=11, write_csv=False)
+    assert np.array_equal(r2["counters"], r["counters"])
+
+
+def test_run_simulation_ensemble_expurgated(S, oracle):
+    import iib_project_ldpc_codes_b200 as L
+    p = {"BEC": 0.40, "expurgation": 0, "num_tests": 1000, "iterations": 40, "n": 240, "dv": 3, "dc": 6,
+         "optimal": False, "message_passing": True, "seed": 3}
+    r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4)
+    # rebuild the same graphs and feed the reference frame loop the same frames
+    want = np.zeros(46, dtype=np.uint64)
+    graphs = (r["num_tests"] + 127) // 128
+    left = r["num_tests"]
+    for gi in range(graphs):
+        vl, cl = L.generate_graph(240, 3, 6, seed=3 * 1000003 + gi, mode=1)
+        cnt = min(128, left); left -= cnt
+        want += oracle.best().mc_run(vl, cl, 240, 120, 3, 6, [0.40], 3, gi * 128, cnt, 40, 0, nthreads=2)[0]
+    assert np.array_equal(r["counters"], want)
+    assert "regular_code_expurgated=0_BEC=0.4_n=240" in r["filename"]
+
+
+def test_cli_modes(S):
+    r = S.main(["prog", "0.35", "256", "30", "120", "3", "6", "3", "1"])
+    assert r["num_tests"] == 256
+    with pytest.raises(NotImplementedError):
+        S.main(["prog", "0.35", "256", "30", "120", "3", "6", "4", "1"])
+    with pytest.raises(ValueError):
+        S.main(["prog", "0.35", "256", "30", "120", "3", "6", "9", "1"])
