@@ -114,6 +114,15 @@ class Graph:
     def set_tuning(self, words=0, teams=0, team_warps=0):
         check(self._lib.ldpc_b200_set_tuning(self._h, words, teams, team_warps))
 
+    def set_place_effort(self, effort):
+        check(self._lib.ldpc_b200_set_place_effort(self._h, effort))
+
+    def placement_info(self, words):
+        a, b, c = ct.c_double(), ct.c_double(), ct.c_double()
+        check(self._lib.ldpc_b200_placement_info(self._h, words, ct.byref(a), ct.byref(b), ct.byref(c)))
+        return {"gather_wavefronts_natural": a.value, "gather_wavefronts_placed": b.value,
+                "gather_wavefronts_ideal": c.value}
+
     # ---- fused Monte-Carlo ----------------------------------------------------------------------
     def mc_run(self, eps, seed, num_frames, iterations, expurgation=-1, first_frame=0, return_stats=False):
         """Host-buffer call: returns uint64 [npoints][iterations+6] (and the launch statistics)."""

@@ -10,7 +10,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OUT = os.path.join(PKG_DIR, "libldpc_b200.so")
-SOURCES = ["ldpc_b200.cu", "graphgen.cpp"]
+SOURCES = ["ldpc_b200.cu", "graphgen.cpp", "relabel.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -44,6 +44,7 @@ struct E1Params {
     // graph (global memory, socket-major uint16: idx[j * pad + node])
     const uint16_t* c2v;
     const uint16_t* v2c;
+    const uint16_t* var_orig;  // slot -> original variable id (keys the erasure generator); NULL = identity
     int n, m, dv, dc, n_pad, m_pad;
     // geometry
     int team_warps, teams;
@@ -197,8 +198,9 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
     cnt = 0u;
     for (int i = t.tid; i < P.n; i += t.nthr) {
         VecT<WORDS> xi;
+        const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
         LDPC_FORW {
-            xi.a[w] = bec_word(bp, point, q0 + w, (uint32_t)i) & valid[w];
+            xi.a[w] = bec_word(bp, point, q0 + w, var) & valid[w];
             red[w] |= xi.a[w];
             cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
         }

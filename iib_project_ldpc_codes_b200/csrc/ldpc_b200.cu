@@ -15,6 +15,7 @@
 
 #include "../../include/ldpc_b200.h"
 #include "e1_kernels.cuh"
+#include "relabel.hpp"
 
 using namespace ldpc;
 
@@ -64,6 +65,13 @@ struct ldpc_b200_graph {
     uint16_t* d_c2v16 = nullptr;   // socket-major [dc][m_pad]
     uint16_t* d_v2c16 = nullptr;   // socket-major [dv][n_pad]
     int sm_count = 0, smem_optin = 0;
+    // bank-conflict-aware placements for the Monte-Carlo kernel, one per words-per-group (index = words)
+    struct Placed {
+        bool ready = false;
+        uint16_t* d_c2v = nullptr; uint16_t* d_v2c = nullptr; uint16_t* d_var_orig = nullptr;
+        double wf_natural = 0, wf_placed = 0, wf_ideal = 0;
+    } placed[5];
+    int place_effort = -1;  // -1: LDPC_B200_PLACE_EFFORT or default
     // workspace
     unsigned long long* d_work = nullptr;
     unsigned long long* d_raw = nullptr; size_t raw_cap = 0;
@@ -209,8 +217,27 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     cudaSetDevice(g->device);
     cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
     cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
+    for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
+}
+
+extern "C" int ldpc_b200_set_place_effort(ldpc_b200_graph* g, int effort) {
+    if (!g) return fail(LDPC_B200_EINVAL, "set_place_effort: NULL graph");
+    g->place_effort = effort;
+    for (auto& pl : g->placed) {
+        cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig);
+        pl = ldpc_b200_graph::Placed();
+    }
+    return LDPC_B200_OK;
+}
+
+extern "C" int ldpc_b200_placement_info(ldpc_b200_graph* g, int words, double* natural, double* placed, double* ideal) {
+    if (!g || words < 1 || words > 4 || !g->placed[words].ready) return fail(LDPC_B200_EINVAL, "placement_info: no placement for words=%d yet", words);
+    if (natural) *natural = g->placed[words].wf_natural;
+    if (placed) *placed = g->placed[words].wf_placed;
+    if (ideal) *ideal = g->placed[words].wf_ideal;
+    return LDPC_B200_OK;
 }
 
 extern "C" int ldpc_b200_set_tuning(ldpc_b200_graph* g, int words, int teams, int team_warps) {
@@ -270,6 +297,29 @@ static int ensure_events(ldpc_b200_graph* g) {
     return LDPC_B200_OK;
 }
 
+// Build (once) the shared-memory placement of the graph for `words` words per node (relabel.hpp).
+static int ensure_placement(ldpc_b200_graph* g, int words) {
+    ldpc_b200_graph::Placed& pl = g->placed[words];
+    if (pl.ready) return LDPC_B200_OK;
+    int effort = g->place_effort;
+    if (effort < 0) { const char* s = getenv("LDPC_B200_PLACE_EFFORT"); effort = s ? atoi(s) : 2; }
+    Placement P;
+    place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, P);
+    std::vector<uint16_t> h_c((size_t)g->dc * g->m_pad, 0), h_v((size_t)g->dv * g->n_pad, 0), h_o((size_t)g->n_pad, 0);
+    for (int c = 0; c < g->m; c++) for (int j = 0; j < g->dc; j++) h_c[(size_t)j * g->m_pad + c] = (uint16_t)P.c2v[(size_t)c * g->dc + j];
+    for (int i = 0; i < g->n; i++) for (int j = 0; j < g->dv; j++) h_v[(size_t)j * g->n_pad + i] = (uint16_t)P.v2c[(size_t)i * g->dv + j];
+    for (int i = 0; i < g->n; i++) h_o[i] = (uint16_t)P.var_orig[i];
+    const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16), bo = align_up((uint32_t)(h_o.size() * 2), 16);
+    CUDA_TRY(cudaMalloc(&pl.d_c2v, bc)); CUDA_TRY(cudaMalloc(&pl.d_v2c, bv)); CUDA_TRY(cudaMalloc(&pl.d_var_orig, bo));
+    CUDA_TRY(cudaMemset(pl.d_c2v, 0, bc)); CUDA_TRY(cudaMemset(pl.d_v2c, 0, bv));
+    CUDA_TRY(cudaMemcpy(pl.d_c2v, h_c.data(), h_c.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_v2c, h_v.data(), h_v.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_var_orig, h_o.data(), h_o.size() * 2, cudaMemcpyHostToDevice));
+    pl.wf_natural = P.wavefronts_natural; pl.wf_placed = P.wavefronts_placed; pl.wf_ideal = P.wavefronts_ideal;
+    pl.ready = true;
+    return LDPC_B200_OK;
+}
+
 extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
                                    uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
                                    uint64_t* d_counters, void* stream) {
@@ -304,8 +354,13 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     CUDA_TRY(cudaMemsetAsync(g->d_raw, 0, raw_words * 8, st));
     CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
 
+    {
+        int rcp = ensure_placement(g, cfg.words);
+        if (rcp) return rcp;
+    }
     E1Params P;
     fill_params(g, cfg, cap, P);
+    P.c2v = g->placed[cfg.words].d_c2v; P.v2c = g->placed[cfg.words].d_v2c; P.var_orig = g->placed[cfg.words].d_var_orig;
     const unsigned long long W = 32ull * cfg.words;
     P.bec = g->d_bec; P.npoints = npoints; P.expurgation = expurgation;
     P.first_word = first_frame / 32; P.num_frames = num_frames;

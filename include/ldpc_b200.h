@@ -120,6 +120,13 @@ int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32
  * in GB/s: the roofline denominator of the shared-memory-resident engine. */
 int ldpc_b200_smem_probe(int device, double *gbytes_per_s);
 
+/* Shared-memory placement of the graph for the Monte-Carlo kernel (csrc/relabel.hpp): effort 0 keeps
+ * the caller's node numbering, >= 1 searches a bank-conflict-free numbering + socket order (default 2,
+ * or LDPC_B200_PLACE_EFFORT).  Results do not depend on it.  placement_info reports the gather
+ * wavefronts per flooding iteration of the natural / chosen / conflict-free layouts. */
+int ldpc_b200_set_place_effort(ldpc_b200_graph *g, int effort);
+int ldpc_b200_placement_info(ldpc_b200_graph *g, int words, double *natural, double *placed, double *ideal);
+
 /* Tuning overrides (0 = automatic): words in {1,2,4}, teams per CTA, warps per team. */
 int ldpc_b200_set_tuning(ldpc_b200_graph *g, int words, int teams, int team_warps);
 

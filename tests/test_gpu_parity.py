@@ -285,8 +285,8 @@ def test_full_size_properties_c2(L):
     vl, cl = L.generate_graph(10000, 3, 6, seed=1, mode=1)
     g = L.Graph(vl, cl)
     its, frames = 200, 200000
-    c = g.mc_run([0.38, 0.43], 12345, frames, its)
-    for row, eps in zip(c, (0.38, 0.43)):
+    c = g.mc_run([0.38, 0.47], 12345, frames, its)
+    for row, eps in zip(c, (0.38, 0.47)):
         hist = row[: its + 1].astype(np.int64)
         assert (np.diff(hist) <= 0).all()                       # erasure counts never grow
         assert row[its + 3] == frames == row[its + 4]
@@ -294,4 +294,4 @@ def test_full_size_properties_c2(L):
         assert abs(hist[0] / (frames * 10000) - eps) < 1e-4     # channel rate
         assert frames <= row[its + 5] <= frames * its           # executed iterations
     assert c[0][its + 1] == 0                                   # eps=0.38 << threshold: every frame decodes
-    assert c[1][its + 1] == frames                              # eps=0.43 > threshold 0.4294: none does
+    assert c[1][its + 1] == frames                              # eps=0.47 >> threshold 0.4294: none does
