@@ -114,6 +114,10 @@ class Graph:
     def set_tuning(self, words=0, teams=0, team_warps=0):
         check(self._lib.ldpc_b200_set_tuning(self._h, words, teams, team_warps))
 
+    def set_engine(self, engine):
+        """0 = automatic, 1 = shared-memory engine (E1), 2 = HBM/L2-streamed engine (E2)."""
+        check(self._lib.ldpc_b200_set_engine(self._h, engine))
+
     def set_place_effort(self, effort):
         check(self._lib.ldpc_b200_set_place_effort(self._h, effort))
 

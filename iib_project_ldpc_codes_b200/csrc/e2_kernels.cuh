@@ -1,0 +1,357 @@
+// e2_kernels.cuh -- "E2": HBM/L2-streamed bit-sliced BEC flooding decoder for graphs that do not fit
+// in shared memory (BASELINE config 3: n = 10^6), sm_100a.
+//
+// Same algorithm as E1 (message_passing.c:7-82 collapsed to OR/AND on bit-sliced words), different
+// memory plan:
+//   * state is FRAME-MINOR in global memory: X[n][R], T[m][R] 32-bit words, R words = 32*R frames per
+//     node row (R = 32 -> 128-byte rows, 1024 frames in lock step).  A thread owns one 128-bit quad
+//     of a row; the 8 lanes of a quarter warp read one full 128-byte row: every gather is a perfectly
+//     coalesced, vectorised ld.global.v4 of four whole 32-byte sectors.
+//   * index arrays (int32, the reference layouts [m][dc], [n][dv]) are streamed once per iteration
+//     and amortised over the 32*R frames of the batch.
+//   * one COOPERATIVE persistent kernel per launch: check phase | grid.sync | variable phase |
+//     grid.sync per iteration, termination decided on the device from OR-reduced masks.
+// Bound: HBM bandwidth (state 1.5*n*R*4 B = 192 MB at n = 10^6, R = 32, larger than L2).
+#pragma once
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include "bec_rng.cuh"
+#include "e1_kernels.cuh"   // raw_stride, red_add
+
+namespace ldpc {
+namespace cg = cooperative_groups;
+
+constexpr int E2_RMAX = 32;
+constexpr int E2_THREADS = 256;
+constexpr int E2_COUNT_SLICE = 4080;  // variables per thread in the per-frame count phase (16 * 255)
+
+struct E2Params {
+    const int* c2v;   // [m][dc]
+    const int* v2c;   // [n][dv]
+    int n, m, dv, dc;
+    int R;            // words per row (multiple of 4, <= 32)
+    uint4* X;         // [n][R/4]
+    uint4* T;         // [m][R/4]
+    uint4* V;         // value plane [n][R/4]   (VALUES)
+    uint4* PAR;       // [m][R/4]               (VALUES)
+    // control block in global memory (uint32): acc[2][2*RMAX + 1]  (any[R], chg[R], cnt)
+    uint32_t* acc;
+    uint32_t* framecnt;     // [32*RMAX] per-frame erased counts (decode mode / expurgation)
+    // Monte-Carlo
+    const BecParams* bec;
+    int npoints, cap, expurgation;
+    unsigned long long first_word, num_frames, batches_per_point;
+    unsigned long long* counters;   // raw layout of e1_kernels.cuh
+    // decode
+    unsigned long long* hbuf;       // [cap+2] per-batch erasure sums, flushed when the batch counts
+    // decode
+    int* errors;   // [frames][cap]
+    int* ret;      // [frames]
+    unsigned long long frame_base;  // first frame of this batch in errors/ret
+};
+
+__device__ __forceinline__ uint32_t& q_at(uint4& v, int k) { return reinterpret_cast<uint32_t*>(&v)[k]; }
+
+// OR-reduce per word column and add-reduce cnt over the block, then one global atomic per column.
+__device__ __forceinline__ void e2_block_accumulate(uint32_t* s_or /*[2*RMAX]*/, uint32_t* s_cnt, uint32_t* g_acc,
+                                                    int R, int q, const uint4& any, const uint4& chg, uint32_t cnt) {
+    // s_or zeroed by caller before the phase
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = reinterpret_cast<const uint32_t*>(&any)[k], c = reinterpret_cast<const uint32_t*>(&chg)[k];
+        if (a) atomicOr(&s_or[q * 4 + k], a);
+        if (c) atomicOr(&s_or[E2_RMAX + q * 4 + k], c);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
+    __syncthreads();
+    for (int k = threadIdx.x; k < R; k += blockDim.x) {
+        if (s_or[k]) atomicOr(&g_acc[k], s_or[k]);
+        if (s_or[E2_RMAX + k]) atomicOr(&g_acc[E2_RMAX + k], s_or[E2_RMAX + k]);
+    }
+    if (threadIdx.x == 0 && *s_cnt) atomicAdd(&g_acc[2 * E2_RMAX], *s_cnt);
+}
+
+template <bool VALUES>
+__device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads) {
+    const int Q = P.R >> 2;
+    const unsigned long long total = (unsigned long long)P.m * Q;
+    for (unsigned long long t = gtid; t < total; t += gthreads) {
+        const int c = (int)(t / Q), q = (int)(t - (unsigned long long)c * Q);
+        uint4 one = make_uint4(0, 0, 0, 0), two = one, par = one;
+        const int* idx = P.c2v + (size_t)c * P.dc;
+        for (int j = 0; j < P.dc; j++) {
+            const int v = __ldg(idx + j);
+            const uint4 w = P.X[(size_t)v * Q + q];
+            two.x |= one.x & w.x; two.y |= one.y & w.y; two.z |= one.z & w.z; two.w |= one.w & w.w;
+            one.x |= w.x; one.y |= w.y; one.z |= w.z; one.w |= w.w;
+            if (VALUES) {
+                const uint4 vv = P.V[(size_t)v * Q + q];
+                par.x ^= vv.x; par.y ^= vv.y; par.z ^= vv.z; par.w ^= vv.w;
+            }
+        }
+        P.T[t] = two;
+        if (VALUES) P.PAR[t] = par;
+    }
+}
+
+template <bool VALUES>
+__device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads,
+                                             const uint32_t* s_mask, uint32_t* s_or, uint32_t* s_cnt, uint32_t* g_acc) {
+    const int Q = P.R >> 2;
+    const unsigned long long total = (unsigned long long)P.n * Q;
+    uint4 any = make_uint4(0, 0, 0, 0), chg = any;
+    uint32_t cnt = 0;
+    int myq = 0;
+    // gthreads is a multiple of Q (host guarantees), so a thread keeps the same quad column
+    for (unsigned long long t = gtid; t < total; t += gthreads) {
+        const int i = (int)(t / Q), q = (int)(t - (unsigned long long)i * Q);
+        myq = q;
+        const uint4 xi = P.X[t];
+        uint4 xn = xi, nv = make_uint4(0, 0, 0, 0);
+        const int* idx = P.v2c + (size_t)i * P.dv;
+        for (int j = 0; j < P.dv; j++) {
+            const int c = __ldg(idx + j);
+            const uint4 tw = P.T[(size_t)c * Q + q];
+            xn.x &= tw.x; xn.y &= tw.y; xn.z &= tw.z; xn.w &= tw.w;
+            if (VALUES) {
+                const uint4 pr = P.PAR[(size_t)c * Q + q];
+                nv.x = (nv.x & tw.x) | (pr.x & ~tw.x); nv.y = (nv.y & tw.y) | (pr.y & ~tw.y);
+                nv.z = (nv.z & tw.z) | (pr.z & ~tw.z); nv.w = (nv.w & tw.w) | (pr.w & ~tw.w);
+            }
+        }
+        if (xn.x != xi.x || xn.y != xi.y || xn.z != xi.z || xn.w != xi.w) {
+            P.X[t] = xn;
+            if (VALUES) {
+                uint4 vi = P.V[t];
+                vi.x |= nv.x & xi.x & ~xn.x; vi.y |= nv.y & xi.y & ~xn.y; vi.z |= nv.z & xi.z & ~xn.z; vi.w |= nv.w & xi.w & ~xn.w;
+                P.V[t] = vi;
+            }
+        }
+        any.x |= xn.x; any.y |= xn.y; any.z |= xn.z; any.w |= xn.w;
+        chg.x |= xi.x ^ xn.x; chg.y |= xi.y ^ xn.y; chg.z |= xi.z ^ xn.z; chg.w |= xi.w ^ xn.w;
+        cnt += __popc(xn.x & s_mask[q * 4]) + __popc(xn.y & s_mask[q * 4 + 1]) + __popc(xn.z & s_mask[q * 4 + 2]) +
+               __popc(xn.w & s_mask[q * 4 + 3]);
+    }
+    e2_block_accumulate(s_or, s_cnt, g_acc, P.R, myq, any, chg, cnt);
+}
+
+// per-frame erased counts of the current state -> framecnt[32*R] (atomicAdd; zeroed beforehand)
+__device__ __forceinline__ void e2_count_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads) {
+    const uint32_t* X = reinterpret_cast<const uint32_t*>(P.X);
+    const int slices = (P.n + E2_COUNT_SLICE - 1) / E2_COUNT_SLICE;
+    const unsigned long long total = (unsigned long long)slices * P.R;
+    for (unsigned long long t = gtid; t < total; t += gthreads) {
+        const int s = (int)(t / P.R), w = (int)(t - (unsigned long long)s * P.R);
+        uint32_t cnt[32];
+#pragma unroll
+        for (int b = 0; b < 32; b++) cnt[b] = 0;
+        const int i1 = min(P.n, (s + 1) * E2_COUNT_SLICE);
+        for (int i0 = s * E2_COUNT_SLICE; i0 < i1; i0 += 255) {
+            uint32_t by[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) by[k] = 0;
+            const int ie = min(i1, i0 + 255);
+            for (int i = i0; i < ie; i++) {
+                const uint32_t xw = X[(size_t)i * P.R + w];
+#pragma unroll
+                for (int k = 0; k < 8; k++) by[k] += (xw >> k) & 0x01010101u;   // bit k+8j -> byte j
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) cnt[k + 8 * j] += (by[k] >> (8 * j)) & 0xFFu;
+        }
+#pragma unroll
+        for (int b = 0; b < 32; b++)
+            if (cnt[b]) atomicAdd(&P.framecnt[w * 32 + b], cnt[b]);
+    }
+}
+
+template <bool VALUES, bool DECODE>
+__global__ void __launch_bounds__(E2_THREADS) e2_kernel(const __grid_constant__ E2Params P) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_or[2 * E2_RMAX];
+    __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_mask[E2_RMAX];     // frames whose erasures are summed (counted frames)
+    __shared__ uint32_t s_running[E2_RMAX];
+    __shared__ uint32_t s_valid[E2_RMAX];
+    __shared__ uint32_t s_any[E2_RMAX];
+    __shared__ uint32_t s_flag;
+
+    const int R = P.R, Q = R >> 2;
+    const int ACC = 2 * E2_RMAX + 1;
+    const unsigned long long gthreads = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool lead = (blockIdx.x == 0 && threadIdx.x == 0);
+    const int stride = raw_stride(P.cap);
+    const unsigned long long items = DECODE ? 1ull : (unsigned long long)P.npoints * P.batches_per_point;
+    int par = 0;   // accumulator buffer the next phase adds into (host zeroes both before the launch)
+
+    auto zero_block_acc = [&]() {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 2 * E2_RMAX; k += blockDim.x) s_or[k] = 0;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    };
+    auto zero_global_acc = [&](int which) {   // block 0 only
+        if (blockIdx.x == 0)
+            for (int k = threadIdx.x; k < ACC; k += blockDim.x) P.acc[which * ACC + k] = 0;
+    };
+
+    for (unsigned long long item = 0; item < items; item++) {
+        const uint32_t point = DECODE ? 0u : (uint32_t)(item / P.batches_per_point);
+        const unsigned long long batch = DECODE ? 0ull : item - (unsigned long long)point * P.batches_per_point;
+        const unsigned long long q0 = P.first_word + batch * R;
+        unsigned long long* C = DECODE ? nullptr : P.counters + (size_t)point * stride;
+        __syncthreads();
+        for (int w = threadIdx.x; w < R; w += blockDim.x) {
+            const unsigned long long f0 = (batch * R + w) * 32ull;
+            const uint32_t v = f0 >= P.num_frames ? 0u
+                               : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+            s_valid[w] = v; s_mask[w] = v;
+        }
+        __syncthreads();
+        if (DECODE && blockIdx.x == 0)
+            for (int f = threadIdx.x; f < 32 * R; f += blockDim.x)
+                if ((s_valid[f >> 5] >> (f & 31)) & 1u) P.ret[P.frame_base + f] = P.cap;
+
+        bool second_pass = false;
+        unsigned long long exec_sum = 0, phys = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            // ---- initial state (channels.py:24-26 drawn in place) and its erased count
+            zero_block_acc();
+            if (!DECODE) {
+                const BecParams bp = P.bec[point];
+                uint4 any = make_uint4(0, 0, 0, 0), chg = any;
+                uint32_t cnt0 = 0;
+                int myq = 0;
+                const unsigned long long total = (unsigned long long)P.n * Q;
+                for (unsigned long long t = gtid; t < total; t += gthreads) {
+                    const int i = (int)(t / Q), q = (int)(t - (unsigned long long)i * Q);
+                    myq = q;
+                    uint4 xi;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t wv = bec_word(bp, point, q0 + q * 4 + k, (uint32_t)i) & s_valid[q * 4 + k];
+                        q_at(xi, k) = wv;
+                        q_at(any, k) |= wv;
+                        cnt0 += __popc(wv & s_mask[q * 4 + k]);
+                    }
+                    P.X[t] = xi;
+                }
+                e2_block_accumulate(s_or, &s_cnt, P.acc + par * ACC, R, myq, any, chg, cnt0);
+            }
+            zero_global_acc(par ^ 1);
+            // framecnt is read by every block when the expurgation mask is formed at the end of pass 0,
+            // so it is only cleared at the start of an item (the previous item ended with a grid.sync)
+            if (blockIdx.x == 0 && pass == 0) for (int f = threadIdx.x; f < 32 * E2_RMAX; f += blockDim.x) P.framecnt[f] = 0;
+            grid.sync();
+            uint32_t cur_cnt = DECODE ? 0u : __ldcg(&P.acc[par * ACC + 2 * E2_RMAX]);   // erased count of the summed frames
+            __syncthreads();
+            for (int w = threadIdx.x; w < R; w += blockDim.x) {
+                s_any[w] = DECODE ? s_valid[w] : __ldcg(&P.acc[par * ACC + w]);
+                s_running[w] = pass == 0 ? s_valid[w] : s_mask[w];
+            }
+            if (!DECODE && lead) P.hbuf[0] = cur_cnt;
+            __syncthreads();
+            par ^= 1;
+
+            int it = 0;
+            for (; it < P.cap; it++) {
+                if (threadIdx.x == 0) { uint32_t r = 0; for (int w = 0; w < R; w++) r |= s_running[w]; s_flag = r; }
+                __syncthreads();
+                if (s_flag == 0u) break;
+                if (pass == 0) for (int w = 0; w < R; w++) exec_sum += __popc(s_running[w]);
+                if (DECODE && blockIdx.x == 0)   // only block 0 reads framecnt, and it is past those reads
+                    for (int f = threadIdx.x; f < 32 * E2_RMAX; f += blockDim.x) P.framecnt[f] = 0;
+                e2_check_phase<VALUES>(P, gtid, gthreads);
+                zero_block_acc();
+                grid.sync();
+                e2_var_phase<VALUES>(P, gtid, gthreads, s_mask, s_or, &s_cnt, P.acc + par * ACC);
+                zero_global_acc(par ^ 1);   // everyone finished reading it before the sync above
+                grid.sync();
+                if (DECODE) {
+                    e2_count_phase(P, gtid, gthreads);
+                    grid.sync();
+                }
+                const uint32_t* A = P.acc + par * ACC;
+                cur_cnt = __ldcg(&A[2 * E2_RMAX]);
+                if (!DECODE && lead) P.hbuf[it + 1] = cur_cnt;
+                if (DECODE && blockIdx.x == 0) {
+                    for (int f = threadIdx.x; f < 32 * R; f += blockDim.x) {
+                        const int w = f >> 5, b = f & 31;
+                        if ((s_valid[w] >> b) & 1u) {
+                            const unsigned long long fr = P.frame_base + f;
+                            P.errors[fr * (unsigned long long)P.cap + it] = (int)__ldcg(&P.framecnt[f]);      // :70-75
+                            if (((s_running[w] >> b) & 1u) && !((__ldcg(&A[w]) >> b) & 1u) && P.ret[fr] == P.cap) P.ret[fr] = it;  // :76-78
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int w = threadIdx.x; w < R; w += blockDim.x) {
+                    s_any[w] = __ldcg(&A[w]);
+                    s_running[w] &= __ldcg(&A[w]) & (it == 0 ? 0xFFFFFFFFu : __ldcg(&A[E2_RMAX + w]));   // message_passing.c:16-19
+                }
+                __syncthreads();
+                par ^= 1;
+            }
+            phys += (unsigned long long)it * 32ull * R;
+
+            if (DECODE) {
+                // skipped iterations copy the last count (:16-19); decoded frames keep the caller's zeros
+                if (blockIdx.x == 0) {
+                    for (int f = threadIdx.x; f < 32 * R; f += blockDim.x) {
+                        const int w = f >> 5, b = f & 31;
+                        if ((s_valid[w] >> b) & 1u) {
+                            const unsigned long long fr = P.frame_base + f;
+                            const int c = it > 0 ? (int)__ldcg(&P.framecnt[f]) : 0;
+                            for (int j = it; j < P.cap; j++) P.errors[fr * (unsigned long long)P.cap + j] = c;
+                        }
+                    }
+                }
+                break;
+            }
+
+            // ---- expurgation predicate (parallel_simulator_expurgated.py:238), decided identically by
+            //      every block from global values
+            if (pass == 0 && P.expurgation >= 0) {
+                e2_count_phase(P, gtid, gthreads);
+                grid.sync();
+                uint32_t kall = 0, kany = 0;
+                __syncthreads();
+                for (int w = 0; w < R; w++) {
+                    uint32_t k = 0;
+                    for (int b = 0; b < 32; b++) k |= (uint32_t)((int)__ldcg(&P.framecnt[w * 32 + b]) > P.expurgation) << b;
+                    k &= s_valid[w];
+                    kall |= k ^ s_valid[w]; kany |= k;
+                    if (threadIdx.x == 0) s_mask[w] = k;
+                }
+                __syncthreads();
+                if (kany == 0u) {
+                    if (lead) {
+                        uint32_t nv = 0; for (int w = 0; w < R; w++) nv += __popc(s_valid[w]);
+                        red_add(C + P.cap + 3, nv); red_add(C + P.cap + 5, exec_sum); red_add(C + 2 * P.cap + 8, phys);
+                    }
+                    break;
+                }
+                if (kall != 0u) { second_pass = true; continue; }   // mixed batch: re-decode with masked sums
+            }
+            if (lead) {
+                for (int b = 0; b <= it; b++) red_add(C + b, __ldcg(&P.hbuf[b]));
+                if (it < P.cap) red_add(C + P.cap + 6 + it + 1, cur_cnt);   // later bins keep the residual
+                uint32_t blk = 0, nk = 0, nv = 0;
+                for (int w = 0; w < R; w++) { blk += __popc(s_any[w] & s_mask[w]); nk += __popc(s_mask[w]); nv += __popc(s_valid[w]); }
+                red_add(C + P.cap + 1, blk);
+                red_add(C + P.cap + 2, cur_cnt);
+                red_add(C + P.cap + 3, nv); red_add(C + P.cap + 4, nk); red_add(C + P.cap + 5, exec_sum);
+                red_add(C + 2 * P.cap + 8, phys);
+                if (second_pass) red_add(C + 2 * P.cap + 9, 1ull);
+            }
+            break;
+        }
+        grid.sync();   // state buffers, framecnt and hbuf are reused by the next item
+    }
+}
+
+}  // namespace ldpc

@@ -16,6 +16,7 @@
 #include "../../include/ldpc_b200.h"
 #include "e1_kernels.cuh"
 #include "relabel.hpp"
+#include "e2_kernels.cuh"
 
 using namespace ldpc;
 
@@ -72,6 +73,13 @@ struct ldpc_b200_graph {
         double wf_natural = 0, wf_placed = 0, wf_ideal = 0;
     } placed[5];
     int place_effort = -1;  // -1: LDPC_B200_PLACE_EFFORT or default
+    // E2 (HBM/L2-streamed engine): int32 lookups in the reference layouts + frame-minor state rows
+    int* d_c2v32 = nullptr; int* d_v2c32 = nullptr;
+    void* e2_X = nullptr; void* e2_T = nullptr; void* e2_V = nullptr; void* e2_PAR = nullptr;
+    size_t e2_xbytes = 0, e2_vbytes = 0;
+    uint32_t* e2_acc = nullptr; uint32_t* e2_framecnt = nullptr;
+    unsigned long long* e2_hbuf = nullptr; size_t e2_hbuf_cap = 0;
+    int engine = 0;  // 0 auto, 1 force E1, 2 force E2
     // workspace
     unsigned long long* d_work = nullptr;
     unsigned long long* d_raw = nullptr; size_t raw_cap = 0;
@@ -218,6 +226,8 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
     cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
     for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
+    cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
+    cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
 }
@@ -237,6 +247,18 @@ extern "C" int ldpc_b200_placement_info(ldpc_b200_graph* g, int words, double* n
     if (natural) *natural = g->placed[words].wf_natural;
     if (placed) *placed = g->placed[words].wf_placed;
     if (ideal) *ideal = g->placed[words].wf_ideal;
+    return LDPC_B200_OK;
+}
+
+static int want_engine(const ldpc_b200_graph* g) {
+    if (g->engine) return g->engine;
+    const int e = tuning_env("LDPC_B200_ENGINE");
+    return (e == 1 || e == 2) ? e : 0;
+}
+
+extern "C" int ldpc_b200_set_engine(ldpc_b200_graph* g, int engine) {
+    if (!g || engine < 0 || engine > 2) return fail(LDPC_B200_EINVAL, "set_engine: engine must be 0 (auto), 1 (shared memory) or 2 (streamed)");
+    g->engine = engine;
     return LDPC_B200_OK;
 }
 
@@ -320,6 +342,14 @@ static int ensure_placement(ldpc_b200_graph* g, int words) {
     return LDPC_B200_OK;
 }
 
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+#include "e2_host.inc"
+
 extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
                                    uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
                                    uint64_t* d_counters, void* stream) {
@@ -332,8 +362,11 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     if (num_frames == 0) return LDPC_B200_OK;
 
     E1Config cfg;
-    if (!plan_e1(g, iterations, false, false, cfg))
-        return fail(LDPC_B200_EUNSUPPORTED, "mc_launch: graph (n=%d dv=%d dc=%d) does not fit the shared-memory engine and the streamed engine is not built", g->n, g->dv, g->dc);
+    const int weng = want_engine(g);
+    const bool fits_e1 = plan_e1(g, iterations, false, false, cfg);
+    if (weng == 1 && !fits_e1)
+        return fail(LDPC_B200_EUNSUPPORTED, "mc_launch: graph (n=%d dv=%d dc=%d) does not fit the shared-memory engine", g->n, g->dv, g->dc);
+    const bool use_e2 = weng == 2 || !fits_e1;
 
     const int cap = iterations;
     const size_t raw_words = (size_t)npoints * raw_stride(cap);
@@ -354,6 +387,22 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     CUDA_TRY(cudaMemsetAsync(g->d_raw, 0, raw_words * 8, st));
     CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
 
+    if (use_e2) {
+        int rc2 = ensure_events(g);
+        if (rc2) return rc2;
+        const int slot2 = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
+        if (slot2 >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot2], st));
+        int grid2 = 0, R2 = 0;
+        rc2 = e2_mc(g, npoints, first_frame, num_frames, cap, expurgation, st, &grid2, &R2);
+        if (rc2) return rc2;
+        if (slot2 >= 0) { CUDA_TRY(cudaEventRecord(g->ev1[slot2], st)); g->ev_count++; }
+        e1_finalize_kernel<<<(npoints + 127) / 128, 128, 0, st>>>(g->d_raw, npoints, cap);
+        mc_compact_kernel<<<npoints, 128, 0, st>>>(g->d_raw, (unsigned long long*)d_counters, g->d_stats, npoints, cap);
+        CUDA_TRY(cudaGetLastError());
+        g->last.engine = 2; g->last.words = R2; g->last.teams = 1; g->last.team_warps = E2_THREADS / 32;
+        g->last.grid = grid2; g->last.smem_bytes = 0;
+        return LDPC_B200_OK;
+    }
     {
         int rcp = ensure_placement(g, cfg.words);
         if (rcp) return rcp;
@@ -450,12 +499,6 @@ static cudaError_t launch_decode(const E1Params& P, int grid, int block, uint32_
     return go(e1_decode_kernel<0, 0, VALUES>);
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-};
-
 extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
                                       int* errors, int* ret) {
     if (!g || !Mvc || !ret || (!errors && iterations > 0)) return fail(LDPC_B200_EINVAL, "decode_batch: NULL argument");
@@ -470,11 +513,25 @@ extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t 
         values |= (s == 1);
     }
     E1Config cfg;
-    if (!plan_e1(g, iterations, values, true, cfg))
-        return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: graph (n=%d dv=%d dc=%d, value plane %s) does not fit the shared-memory engine and the streamed engine is not built",
+    const int weng = want_engine(g);
+    const bool fits_e1 = plan_e1(g, iterations, values, true, cfg);
+    if (weng == 1 && !fits_e1)
+        return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: graph (n=%d dv=%d dc=%d, value plane %s) does not fit the shared-memory engine",
                     g->n, g->dv, g->dc, values ? "on" : "off");
     const uint64_t groups = (frames + 31) / 32;
     DevBuf d_mvc, d_x, d_v, d_err, d_ret;
+    if (weng == 2 || !fits_e1) {
+        CUDA_TRY(d_mvc.alloc(total));
+        CUDA_TRY(d_err.alloc((size_t)frames * iterations * 4));
+        CUDA_TRY(d_ret.alloc((size_t)frames * 4));
+        CUDA_TRY(cudaMemcpy(d_mvc.p, Mvc, total, cudaMemcpyHostToDevice));
+        int rc2 = e2_decode(g, (int8_t*)d_mvc.p, frames, iterations, values, (int*)d_err.p, (int*)d_ret.p);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaMemcpy(Mvc, d_mvc.p, total, cudaMemcpyDeviceToHost));
+        if (iterations > 0) CUDA_TRY(cudaMemcpy(errors, d_err.p, (size_t)frames * iterations * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ret, d_ret.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
+        return LDPC_B200_OK;
+    }
     CUDA_TRY(d_mvc.alloc(total));
     CUDA_TRY(d_x.alloc(groups * g->n * 4));
     CUDA_TRY(d_v.alloc(groups * g->n * 4));

@@ -127,6 +127,9 @@ int ldpc_b200_smem_probe(int device, double *gbytes_per_s);
 int ldpc_b200_set_place_effort(ldpc_b200_graph *g, int effort);
 int ldpc_b200_placement_info(ldpc_b200_graph *g, int words, double *natural, double *placed, double *ideal);
 
+/* Engine override: 0 automatic (shared-memory engine when the graph fits, else streamed), 1 = E1, 2 = E2. */
+int ldpc_b200_set_engine(ldpc_b200_graph *g, int engine);
+
 /* Tuning overrides (0 = automatic): words in {1,2,4}, teams per CTA, warps per team. */
 int ldpc_b200_set_tuning(ldpc_b200_graph *g, int words, int teams, int team_warps);
 
