@@ -30,7 +30,7 @@ class LdpcB200Error(RuntimeError):
 class McStats(ct.Structure):
     _fields_ = [("phys_frame_iterations", ct.c_uint64), ("second_pass_groups", ct.c_uint64),
                 ("engine", ct.c_int32), ("words", ct.c_int32), ("teams", ct.c_int32), ("team_warps", ct.c_int32),
-                ("grid", ct.c_int32), ("smem_bytes", ct.c_int32)]
+                ("grid", ct.c_int32), ("smem_bytes", ct.c_int32), ("stages", ct.c_int32), ("kernel_launches", ct.c_int32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -1,0 +1,271 @@
+// e1_staged.cuh -- staged variant of the E1 Monte-Carlo kernel: survivors are re-packed between stages.
+//
+// A bit-sliced frame group runs in lock step until its slowest frame stops; at n = 1000, eps = 0.40 the
+// reference executes 16.5 iterations per frame on average but the slowest of 128 frames needs 44
+// (SURVEY.md 7.4 "lane inflation", measured 2.68x in profiles/r1a_*).  Frames are independent, so the
+// iteration range [0, cap) is cut into stages [c_s, c_{s+1}) per erasure point: a group that reaches
+// c_{s+1} with frames still running writes those frames (state column, bit-packed frame-major) to an HBM
+// spill buffer and takes new work; the next launch packs 32*WORDS survivors of the SAME age into a dense
+// group and continues.  Everything a frame contributes (per-iteration erasure sums, block/bit errors,
+// executed iterations) is additive, and all frames of a group always have the same age, so the cheap
+// horizontal popcount per iteration stays valid.  Results are bit-identical to the unstaged kernel.
+//
+// 32x32 bit transposes (warp shuffles, 5 butterfly steps) convert between the bit-sliced shared-memory
+// layout (word per node, bit per frame) and the frame-major spill records (word per 32 nodes).
+#pragma once
+#include "e1_kernels.cuh"
+
+namespace ldpc {
+
+// lane l holds row l; afterwards lane b holds column b  (out_b bit l = in_l bit b).  Warp-collective.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t p = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+        x = (lane & j) ? (((p >> j) & m) | (x & ~m)) : ((x & m) | ((p & m) << j));
+    }
+    return x;
+}
+
+struct StageParams {
+    int stage, nstages;
+    const int* cuts;                      // [npoints][nstages+1] ages: stage s covers [cuts[s], cuts[s+1])
+    const uint32_t* spill_in;             // records of the previous stage
+    uint32_t* spill_out;
+    const unsigned long long* cnt_in;     // [npoints] records available per point
+    unsigned long long* cnt_out;          // [npoints] records written per point (atomic)
+    unsigned long long point_stride;      // record capacity per point
+    int rec_words;                        // 32-bit words per record = ceil(n/32) rounded up to 4
+    unsigned long long* stop_hist;        // optional [npoints][cap+1]: frames by executed-iteration count
+};
+
+template <int WORDS, int DV, int DC>
+__global__ void __launch_bounds__(E1_MAX_THREADS, 1)
+e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
+    uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
+    {
+        const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
+        const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
+        const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
+        const uint4* g1 = reinterpret_cast<const uint4*>(P.v2c);
+        uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
+        uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+    }
+    __syncthreads();
+
+    TeamCtx t;
+    t.team_warps = P.team_warps;
+    t.nthr = P.team_warps * 32;
+    const int team = threadIdx.x / t.nthr;
+    t.tid = threadIdx.x - team * t.nthr;
+    t.lane = threadIdx.x & 31;
+    t.warp = t.tid >> 5;
+    t.bar_id = 1 + team;
+    unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
+    VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
+    VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
+    uint32_t* xs = reinterpret_cast<uint32_t*>(x);
+    uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
+    t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
+    uint32_t* work_slot = t.scr + 32 * (2 * WORDS + 1);
+
+    constexpr int W = 32 * WORDS;
+    const int stride = raw_stride(P.cap);
+    const int nst1 = S.nstages + 1;
+
+    unsigned long long total = 0;
+    if (S.stage == 0) total = (unsigned long long)P.npoints * P.groups_per_point;
+    else for (int p = 0; p < P.npoints; p++) total += (S.cnt_in[p] + W - 1) / W;
+
+    for (;;) {
+        unsigned long long item;
+        if (t.team_warps == 1) {
+            unsigned long long v = 0;
+            if (t.lane == 0) v = atomicAdd(P.work_counter, 1ull);
+            item = __shfl_sync(0xFFFFFFFFu, v, 0);
+        } else {
+            if (t.tid == 0) {
+                unsigned long long v = atomicAdd(P.work_counter, 1ull);
+                work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+            }
+            team_sync(t);
+            item = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+            team_sync(t);   // work_slot is reused for the spill base below
+        }
+        if (item >= total) break;
+
+        uint32_t point;
+        unsigned long long gi;
+        uint32_t valid[WORDS];
+        if (S.stage == 0) {
+            point = (uint32_t)(item / P.groups_per_point);
+            gi = item - (unsigned long long)point * P.groups_per_point;
+            LDPC_FORW {
+                const unsigned long long f0 = (gi * WORDS + w) * 32ull;
+                valid[w] = f0 >= P.num_frames ? 0u
+                           : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+            }
+        } else {
+            unsigned long long rest = item;
+            int p = 0;
+            for (; p < P.npoints; p++) {
+                const unsigned long long gp = (S.cnt_in[p] + W - 1) / W;
+                if (rest < gp) break;
+                rest -= gp;
+            }
+            point = (uint32_t)p;
+            gi = rest;
+            const unsigned long long left = S.cnt_in[p] - gi * W;
+            LDPC_FORW {
+                const unsigned long long f0 = (unsigned long long)w * 32ull;
+                valid[w] = f0 >= left ? 0u : (left - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(left - f0)) - 1u));
+            }
+        }
+        const int lo = S.cuts[point * nst1 + S.stage], hi = S.cuts[point * nst1 + S.stage + 1];
+        unsigned long long* C = P.counters + (size_t)point * stride;
+
+        uint32_t any[WORDS], cnt = 0;
+        // ---- initial state of the group
+        if (S.stage == 0) {
+            const BecParams bp = P.bec[point];
+            const unsigned long long q0 = P.first_word + gi * WORDS;
+            uint32_t red[WORDS];
+            LDPC_FORW red[w] = 0u;
+            for (int i = t.tid; i < P.n; i += t.nthr) {
+                VecT<WORDS> xi;
+                const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
+                LDPC_FORW {
+                    xi.a[w] = bec_word(bp, point, q0 + w, var) & valid[w];
+                    red[w] |= xi.a[w];
+                    cnt += __popc(xi.a[w]);
+                }
+                x[i] = xi;
+            }
+            team_reduce<WORDS>(t, red, cnt);
+            LDPC_FORW any[w] = red[w];
+            if (t.tid == 0) hbuf[0] = cnt;
+        } else {
+            const uint32_t* recs = S.spill_in + ((size_t)point * S.point_stride + gi * W) * S.rec_words;
+            for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
+                LDPC_FORW {
+                    uint4 r = make_uint4(0, 0, 0, 0);
+                    if ((valid[w] >> t.lane) & 1u)
+                        r = *reinterpret_cast<const uint4*>(recs + (size_t)(w * 32 + t.lane) * S.rec_words + j0);
+                    const uint32_t c0 = transpose32(r.x, t.lane), c1 = transpose32(r.y, t.lane);
+                    const uint32_t c2 = transpose32(r.z, t.lane), c3 = transpose32(r.w, t.lane);
+                    const int s0 = 32 * j0 + t.lane;
+                    if (s0 < P.n) xs[s0 * WORDS + w] = c0;
+                    if (s0 + 32 < P.n) xs[(s0 + 32) * WORDS + w] = c1;
+                    if (s0 + 64 < P.n) xs[(s0 + 64) * WORDS + w] = c2;
+                    if (s0 + 96 < P.n) xs[(s0 + 96) * WORDS + w] = c3;
+                }
+            }
+            LDPC_FORW any[w] = valid[w];
+            team_sync(t);
+        }
+
+        // ---- iterations [lo, hi) in lock step (message_passing.c:15-78 per frame)
+        uint32_t running[WORDS];
+        LDPC_FORW running[w] = valid[w];
+        unsigned long long exec_sum = 0;
+        int age = lo;
+        for (; age < hi; age++) {
+            uint32_t r = 0u, pc = 0u;
+            LDPC_FORW { r |= running[w]; pc += __popc(running[w]); }
+            if (r == 0u) break;
+            exec_sum += pc;
+            check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
+            team_sync(t);
+            uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
+            var_phase<WORDS, DV, DC, false, false>(P, t, s_v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
+            LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
+            team_reduce<2 * WORDS>(t, oc, cnt);
+            if (t.tid == 0) hbuf[age - lo + 1] = cnt;
+            uint32_t stopped = 0;
+            LDPC_FORW {
+                any[w] = oc[w];
+                const uint32_t nr = running[w] & oc[w] & (age == 0 ? 0xFFFFFFFFu : oc[WORDS + w]);   // :16-19, :76-78
+                stopped += __popc(running[w] & ~nr);
+                running[w] = nr;
+            }
+            if (S.stop_hist && t.tid == 0) red_add(S.stop_hist + (size_t)point * (P.cap + 1) + age + 1, stopped);
+        }
+        // frames still running at a stage boundary below the cap are deferred to the next stage
+        uint32_t D[WORDS], F[WORDS], ndef = 0;
+        LDPC_FORW {
+            D[w] = (age == hi && hi < P.cap) ? running[w] : 0u;
+            F[w] = valid[w] & ~D[w];
+            ndef += __popc(D[w]);
+        }
+        if (S.stop_hist && t.tid == 0 && hi >= P.cap) {
+            uint32_t capped = 0;
+            LDPC_FORW capped += __popc(running[w]);
+            red_add(S.stop_hist + (size_t)point * (P.cap + 1) + P.cap, capped);   // ran every iteration up to the cap
+        }
+        uint32_t resid = cnt;   // erased count of the finished frames
+        if (ndef) {
+            uint32_t none[1] = {0u};
+            resid = 0;
+            for (int i = t.tid; i < P.n; i += t.nthr) {
+                const VecT<WORDS> xi = x[i];
+                LDPC_FORW resid += __popc(xi.a[w] & F[w]);
+            }
+            team_reduce<1>(t, none, resid);
+        }
+        // ---- flush the statistics of this stage
+        team_sync(t);
+        const int first_bin = S.stage == 0 ? 0 : 1;
+        for (int b = first_bin + t.tid; b <= age - lo; b += t.nthr) red_add(C + lo + b, hbuf[b]);
+        if (t.tid == 0) {
+            if (age < P.cap) red_add(C + P.cap + 6 + age + 1, resid);   // bins after `age` keep the finished frames' residual
+            uint32_t blk = 0, nv = 0;
+            LDPC_FORW { blk += __popc(any[w] & F[w]); nv += __popc(valid[w]); }
+            red_add(C + P.cap + 1, blk);
+            red_add(C + P.cap + 2, resid);
+            if (S.stage == 0) { red_add(C + P.cap + 3, nv); red_add(C + P.cap + 4, nv); }
+            red_add(C + P.cap + 5, exec_sum);
+            red_add(C + 2 * P.cap + 8, (unsigned long long)(age - lo) * W);
+        }
+        // ---- spill the deferred frames (bit-packed, frame-major) for the next stage
+        if (ndef) {
+            unsigned long long sbase;
+            if (t.team_warps == 1) {
+                unsigned long long v = 0;
+                if (t.lane == 0) v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+                sbase = __shfl_sync(0xFFFFFFFFu, v, 0);
+            } else {
+                if (t.tid == 0) {
+                    unsigned long long v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+                    work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+                }
+                team_sync(t);
+                sbase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+            }
+            uint32_t* out = S.spill_out + (size_t)point * S.point_stride * S.rec_words;
+            for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
+                uint32_t before = 0;
+                LDPC_FORW {
+                    const int s0 = 32 * j0 + t.lane;
+                    uint4 r;
+                    r.x = transpose32(s0 < P.n ? xs[s0 * WORDS + w] : 0u, t.lane);
+                    r.y = transpose32(s0 + 32 < P.n ? xs[(s0 + 32) * WORDS + w] : 0u, t.lane);
+                    r.z = transpose32(s0 + 64 < P.n ? xs[(s0 + 64) * WORDS + w] : 0u, t.lane);
+                    r.w = transpose32(s0 + 96 < P.n ? xs[(s0 + 96) * WORDS + w] : 0u, t.lane);
+                    if ((D[w] >> t.lane) & 1u) {
+                        const unsigned long long rec = sbase + before + __popc(D[w] & ((1u << t.lane) - 1u));
+                        *reinterpret_cast<uint4*>(out + (size_t)rec * S.rec_words + j0) = r;
+                    }
+                    before += __popc(D[w]);
+                }
+            }
+        }
+        team_sync(t);   // shared state is rewritten by the next group
+    }
+}
+
+}  // namespace ldpc

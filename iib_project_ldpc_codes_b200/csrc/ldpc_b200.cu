@@ -17,6 +17,7 @@
 #include "e1_kernels.cuh"
 #include "relabel.hpp"
 #include "e2_kernels.cuh"
+#include "e1_staged.cuh"
 
 using namespace ldpc;
 
@@ -59,6 +60,12 @@ struct E1Config {
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
 };
 
+struct StagePlan {
+    int nstages = 1;
+    std::vector<int> cuts;   // [npoints][nstages+1]
+    double predicted_inflation = 0;
+};
+
 struct ldpc_b200_graph {
     int n = 0, k = 0, m = 0, dv = 0, dc = 0, device = 0;
     int n_pad = 0, m_pad = 0;
@@ -80,6 +87,13 @@ struct ldpc_b200_graph {
     uint32_t* e2_acc = nullptr; uint32_t* e2_framecnt = nullptr;
     unsigned long long* e2_hbuf = nullptr; size_t e2_hbuf_cap = 0;
     int engine = 0;  // 0 auto, 1 force E1, 2 force E2
+    // staged E1 Monte-Carlo: cut points per (eps list, cap, words), spill buffers, per-stage record counts
+    std::unordered_map<uint64_t, StagePlan> plans;
+    void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0;
+    unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
+    int* d_cuts = nullptr; size_t cuts_cap = 0;
+    int launches = 0;      // kernels launched since the last stats read
+    int last_stages = 1;
     // workspace
     unsigned long long* d_work = nullptr;
     unsigned long long* d_raw = nullptr; size_t raw_cap = 0;
@@ -228,6 +242,7 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
     cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
     cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
+    cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_cuts);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
 }
@@ -349,6 +364,7 @@ struct DevBuf {
 };
 
 #include "e2_host.inc"
+#include "e1_staged_host.inc"
 
 extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
                                    uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
@@ -399,6 +415,7 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
         e1_finalize_kernel<<<(npoints + 127) / 128, 128, 0, st>>>(g->d_raw, npoints, cap);
         mc_compact_kernel<<<npoints, 128, 0, st>>>(g->d_raw, (unsigned long long*)d_counters, g->d_stats, npoints, cap);
         CUDA_TRY(cudaGetLastError());
+        g->launches += 3; g->last_stages = 1;
         g->last.engine = 2; g->last.words = R2; g->last.teams = 1; g->last.team_warps = E2_THREADS / 32;
         g->last.grid = grid2; g->last.smem_bytes = 0;
         return LDPC_B200_OK;
@@ -422,20 +439,38 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
 
     int rc = ensure_events(g);
     if (rc) return rc;
+    // staged path: survivors are re-packed between stages (e1_staged.cuh); exact, used when every frame
+    // counts (no expurgation mask) and the run is long enough to amortise the pilot
+    StagePlan* plan = nullptr;
+    if (expurgation < 0 && num_frames >= 32768 && tuning_env("LDPC_B200_STAGES") != 1) {
+        rc = get_stage_plan(g, cfg, P, eps, npoints, seed, cap, st, &plan);
+        if (rc) return rc;
+        if (plan->nstages <= 1) plan = nullptr;
+    }
     const int slot = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
     if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));
-    cudaError_t e;
-    if (cfg.words == 4) e = launch_mc_words<4>(P, grid, block, cfg.smem, st);
-    else if (cfg.words == 2) e = launch_mc_words<2>(P, grid, block, cfg.smem, st);
-    else e = launch_mc_words<1>(P, grid, block, cfg.smem, st);
-    if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "mc_launch: kernel launch failed: %s", cudaGetErrorString(e));
+    int grid_used = grid;
+    if (plan) {
+        rc = e1_mc_staged(g, cfg, P, *plan, npoints, first_frame, num_frames, st, &grid_used);
+        if (rc) return rc;
+        g->last_stages = plan->nstages;
+    } else {
+        cudaError_t e;
+        if (cfg.words == 4) e = launch_mc_words<4>(P, grid, block, cfg.smem, st);
+        else if (cfg.words == 2) e = launch_mc_words<2>(P, grid, block, cfg.smem, st);
+        else e = launch_mc_words<1>(P, grid, block, cfg.smem, st);
+        if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "mc_launch: kernel launch failed: %s", cudaGetErrorString(e));
+        g->launches += 1;
+        g->last_stages = 1;
+    }
     if (slot >= 0) { CUDA_TRY(cudaEventRecord(g->ev1[slot], st)); g->ev_count++; }
     e1_finalize_kernel<<<(npoints + 127) / 128, 128, 0, st>>>(g->d_raw, npoints, cap);
     mc_compact_kernel<<<npoints, 128, 0, st>>>(g->d_raw, (unsigned long long*)d_counters, g->d_stats, npoints, cap);
     CUDA_TRY(cudaGetLastError());
 
+    g->launches += 2;
     g->last.engine = 1; g->last.words = cfg.words; g->last.teams = cfg.teams; g->last.team_warps = cfg.team_warps;
-    g->last.grid = grid; g->last.smem_bytes = (int)cfg.smem;
+    g->last.grid = grid_used; g->last.smem_bytes = (int)cfg.smem;
     return LDPC_B200_OK;
 }
 
@@ -448,6 +483,9 @@ extern "C" int ldpc_b200_mc_stats_read(ldpc_b200_graph* g, ldpc_b200_mc_stats* s
     *stats = g->last;
     stats->phys_frame_iterations = h[0];
     stats->second_pass_groups = h[1];
+    stats->stages = g->last_stages;
+    stats->kernel_launches = g->launches;
+    g->launches = 0;
     return LDPC_B200_OK;
 }
 

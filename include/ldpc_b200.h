@@ -43,6 +43,8 @@ typedef struct ldpc_b200_mc_stats {
     int32_t team_warps;             /* warps cooperating on one frame group                                */
     int32_t grid;                   /* CTAs launched                                                       */
     int32_t smem_bytes;             /* dynamic shared memory per CTA                                       */
+    int32_t stages;                 /* stages of the last launch (survivor re-packing, 1 = unstaged)       */
+    int32_t kernel_launches;        /* kernels launched since the previous statistics read                 */
 } ldpc_b200_mc_stats;
 
 /* ---- reference drop-ins ------------------------------------------------------------------- */

@@ -36,7 +36,7 @@ for cfg in cfgs:
         ex = int(c[:, cap + 5].sum()); fr = int(c[:, cap + 3].sum())
         print(f"cfg={cfg} words={s['words']} teams={s['teams']} tw={s['team_warps']} grid={s['grid']} smem={s['smem_bytes']} "
               f"ms={ms:.2f} frames/s={fr/ms*1e3:.4g} EU/s={ex*n*dv/ms*1e3:.4g} it/frame={ex/fr:.2f} "
-              f"inflation={s['phys_frame_iterations']/ex:.3f} engine={s['engine']} "
+              f"inflation={s['phys_frame_iterations']/ex:.3f} engine={s['engine']} stages={s['stages']} launches={s['kernel_launches']} "
               f"place={g.placement_info(s['words']) if s['engine'] == 1 else None}", flush=True)
     except Exception as e:  # noqa: BLE001
         print(f"cfg={cfg} failed: {e}", flush=True)
