@@ -24,6 +24,8 @@
 namespace ldpc {
 
 constexpr int E1_MAX_THREADS = 512;
+// one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
+__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : 512; }
 
 template <int WORDS> struct VecT;
 template <> struct alignas(4)  VecT<1> { uint32_t a[1]; };
@@ -237,7 +239,7 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
 }
 
 template <int WORDS, int DV, int DC>
-__global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_mc_kernel(const __grid_constant__ E1Params P) {
+__global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __grid_constant__ E1Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
     uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);

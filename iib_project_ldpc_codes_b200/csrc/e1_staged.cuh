@@ -41,7 +41,7 @@ struct StageParams {
 };
 
 template <int WORDS, int DV, int DC>
-__global__ void __launch_bounds__(E1_MAX_THREADS, 1)
+__global__ void __launch_bounds__(e1_threads(WORDS), 1)
 e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);

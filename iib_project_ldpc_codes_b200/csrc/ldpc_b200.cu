@@ -134,10 +134,11 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
     int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
     int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
     int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
-    const int max_warps = E1_MAX_THREADS / 32;
+
     const int cand[3] = {4, 2, 1};
     for (int ci = 0; ci < 3; ci++) {
         int words = cand[ci];
+        const int max_warps = (decode ? E1_MAX_THREADS : e1_threads(words)) / 32;
         if (decode && words != 1) continue;
         if (want_words && words != want_words) continue;
         E1Config c;

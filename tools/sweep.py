@@ -24,7 +24,7 @@ st = torch.cuda.current_stream().cuda_stream
 for cfg in cfgs:
     g.set_tuning(*cfg)
     try:
-        g.mc_launch(eps, 1, min(frames, 100000), cap, d.data_ptr(), st)
+        g.mc_launch(eps, 1, frames, cap, d.data_ptr(), st)
         torch.cuda.synchronize()
         g.kernel_times_ms(); g.mc_stats()
         d.zero_()
