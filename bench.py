@@ -241,7 +241,9 @@ def main():
                 "note": ("E1 keeps graph+state in shared memory: HBM sees only the counter REDs; peak = shared-memory "
                          "read bandwidth measured on this GPU by ldpc_b200_smem_probe (conflict-free LDS.128 from all SMs)")
                 if e1 else "E2 streams frame-minor state rows and int32 lookups from HBM/L2; peak = measured HBM copy bandwidth",
-                "kernel": "e1_mc_kernel" if e1 else "e2_kernel", "kernel_ms_mean": k_ms,
+                "kernel": (("e1_mc_staged_kernel x%d stages (survivor re-packing), timed as one pipeline" % stats["stages"])
+                           if stats["stages"] > 1 else "e1_mc_kernel") if e1 else "e2_kernel",
+                "kernel_ms_mean": k_ms,
                 "kernel_share_of_step": k_ms * args.steps / ms,
                 "alg_bytes_per_edge_update": b_alg, "alg_bytes_per_launch": alg_bytes_per_launch,
                 "frac_of_hbm_peak": achieved / hbm_peak, "hbm_peak": hbm_peak,
@@ -274,7 +276,7 @@ def main():
             "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_point_per_gpu": frames,
                        "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED, "l2": "256 MiB flush write between steps",
                        "engine": stats},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks}
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks}
 
     if not args.no_cpu_baseline and world >= 1:
         from oracle import oracle as O

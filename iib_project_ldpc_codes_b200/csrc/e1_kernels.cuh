@@ -50,6 +50,7 @@ struct E1Params {
     int n, m, dv, dc, n_pad, m_pad;
     // geometry
     int team_warps, teams;
+    int v2c_global;   // 1: variable-side lookups stay in global memory (not staged into shared memory)
     // shared-memory byte offsets
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride;
     uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
@@ -139,7 +140,9 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
 // ---- variable phase:  x_i &= AND_j two[v2c[i][j]]   (message_passing.c:52-65 collapsed) ----
 // VALUES: a variable resolved in this iteration takes the parity of the LAST listed check that
 // resolves it (message_passing.c:56-61 has no break: last writer wins).
-template <int WORDS, int DV, int DC, bool VALUES, bool MASKED>
+// VG: the variable-side lookups are streamed from global memory / L2 (coalesced, read-only) instead of
+// shared memory, which frees room for a wider frame group when the graph is large (n = 10^4).
+template <int WORDS, int DV, int DC, bool VALUES, bool MASKED, bool VG = false>
 __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, const uint16_t* __restrict__ s_v2c,
                                           VecT<WORDS>* __restrict__ x, const VecT<WORDS>* __restrict__ two,
                                           VecT<WORDS>* __restrict__ val, const VecT<WORDS>* __restrict__ par,
@@ -149,14 +152,14 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
     const int n = P.n, n_pad = P.n_pad;
     LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
     cnt = 0u;
-#pragma unroll 2
+#pragma unroll(VG ? 4 : 2)
     for (int i = t.tid; i < n; i += t.nthr) {
         const VecT<WORDS> xi = x[i];
         VecT<WORDS> xn = xi, nv;
         LDPC_FORW nv.a[w] = 0u;
 #pragma unroll
         for (int j = 0; j < dv; j++) {
-            const int c = s_v2c[j * n_pad + i];
+            const int c = VG ? (int)__ldg(s_v2c + j * n_pad + i) : (int)s_v2c[j * n_pad + i];
             const VecT<WORDS> tw = two[c];
             LDPC_FORW xn.a[w] &= tw.a[w];
             if (VALUES) {
@@ -224,7 +227,8 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
         check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
         team_sync(t);
         uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-        var_phase<WORDS, DV, DC, false, MASKED>(P, t, s_v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
+        if (P.v2c_global) var_phase<WORDS, DV, DC, false, MASKED, true>(P, t, P.v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
+        else var_phase<WORDS, DV, DC, false, MASKED, false>(P, t, s_v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
         LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
         team_reduce<2 * WORDS>(t, oc, cnt);
         if (t.tid == 0) hbuf[it + 1] = cnt;
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
         uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
         for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
-        for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+        if (!P.v2c_global) for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
     }
     __syncthreads();
 

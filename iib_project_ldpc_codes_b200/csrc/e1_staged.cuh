@@ -54,7 +54,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
         uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
         uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
         for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
-        for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+        if (!P.v2c_global) for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
     }
     __syncthreads();
 
@@ -182,7 +182,8 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
             team_sync(t);
             uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-            var_phase<WORDS, DV, DC, false, false>(P, t, s_v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
+            if (P.v2c_global) var_phase<WORDS, DV, DC, false, false, true>(P, t, P.v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
+            else var_phase<WORDS, DV, DC, false, false, false>(P, t, s_v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
             LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
             team_reduce<2 * WORDS>(t, oc, cnt);
             if (t.tid == 0) hbuf[age - lo + 1] = cnt;

@@ -56,6 +56,7 @@ static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a
 struct E1Config {
     int words = 0, teams = 0, team_warps = 0;
     bool values = false;
+    bool v2c_global = false;
     uint32_t smem = 0;
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
 };
@@ -135,17 +136,27 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
     int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
     int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
 
-    const int cand[3] = {4, 2, 1};
-    for (int ci = 0; ci < 3; ci++) {
-        int words = cand[ci];
+    // candidates in order of preference: (words, variable-side lookups streamed from L2?)
+    // A wider group amortises index traffic and instructions over more frames; streaming v2c frees
+    // dv*n*2 bytes of shared memory (n = 10^4: W = 64 fits only that way).
+    struct Cand { int words; bool vg; };
+    const Cand cand[5] = {{4, false}, {2, false}, {2, true}, {1, false}, {1, true}};
+    const int want_vg = tuning_env("LDPC_B200_V2C_GLOBAL");   // 0 auto, 1 force on, 2 force off
+    const uint32_t c2v_bytes = align_up((uint32_t)g->dc * g->m_pad * 2, 16);
+    for (int ci = 0; ci < 5; ci++) {
+        const int words = cand[ci].words;
+        const bool vg = cand[ci].vg;
+        if (vg && (decode || want_vg == 2)) continue;
+        if (!vg && want_vg == 1 && !decode) continue;
         const int max_warps = (decode ? E1_MAX_THREADS : e1_threads(words)) / 32;
         if (decode && words != 1) continue;
         if (want_words && words != want_words) continue;
+        const uint32_t gbytes = vg ? c2v_bytes : graph_bytes;
         E1Config c;
         uint32_t tb = team_bytes(words, c);
-        if (graph_bytes + tb > limit) continue;
-        int fit = (int)((limit - graph_bytes) / tb);
-        const int min_teams = want_words ? 1 : (words == 4 ? 4 : (words == 2 ? 2 : 1));
+        if (gbytes + tb > limit) continue;
+        int fit = (int)((limit - gbytes) / tb);
+        const int min_teams = want_words ? 1 : (words == 4 ? 4 : (words == 2 && !vg ? 2 : 1));
         if (fit < min_teams) continue;
         int teams = std::min(fit, max_warps);
         if (want_teams) teams = std::min(want_teams, fit);
@@ -154,12 +165,12 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
         while (teams * tw > max_warps && tw > 1) tw--;
         if (teams * tw > max_warps) teams = max_warps / tw;
         if (teams < 1) continue;
-        c.words = words; c.teams = teams; c.team_warps = tw; c.values = values;
+        c.words = words; c.teams = teams; c.team_warps = tw; c.values = values; c.v2c_global = vg;
         c.sm_c2v = 0;
-        c.sm_v2c = align_up((uint32_t)g->dc * g->m_pad * 2, 16);
-        c.sm_team0 = graph_bytes;
+        c.sm_v2c = c2v_bytes;
+        c.sm_team0 = gbytes;
         c.sm_team_stride = tb;
-        c.smem = graph_bytes + tb * teams;
+        c.smem = gbytes + tb * teams;
         cfg = c;
         return true;
     }
@@ -170,7 +181,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     memset(&P, 0, sizeof P);
     P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
     P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
-    P.team_warps = c.team_warps; P.teams = c.teams;
+    P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0;
     P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
     P.cap = cap;
