@@ -122,14 +122,37 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
     for (int c = t.tid; c < m; c += t.nthr) {
         VecT<WORDS> one, tw, pr;
         LDPC_FORW { one.a[w] = 0u; tw.a[w] = 0u; pr.a[w] = 0u; }
+        if (DC >= 3 && !VALUES) {
+            // sockets in triples: "some" = a|b|c and "at least two" = majority(a,b,c) are one LOP3 each,
+            // and triples combine with two |= maj | (one & some): 7 logic ops per word for dc = 6 instead
+            // of 12, with a dependency depth of 3 instead of 6
 #pragma unroll
-        for (int j = 0; j < dc; j++) {
-            const int v = s_c2v[j * m_pad + c];
-            const VecT<WORDS> xv = x[v];
-            LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
-            if (VALUES) {
-                const VecT<WORDS> vv = val[v];  // invariant: value bits are 0 where erased
-                LDPC_FORW pr.a[w] ^= vv.a[w];
+            for (int j = 0; j + 2 < DC; j += 3) {
+                const VecT<WORDS> a = x[s_c2v[j * m_pad + c]];
+                const VecT<WORDS> b = x[s_c2v[(j + 1) * m_pad + c]];
+                const VecT<WORDS> d = x[s_c2v[(j + 2) * m_pad + c]];
+                LDPC_FORW {
+                    const uint32_t some = a.a[w] | b.a[w] | d.a[w];
+                    const uint32_t maj = (a.a[w] & b.a[w]) | (a.a[w] & d.a[w]) | (b.a[w] & d.a[w]);
+                    tw.a[w] = tw.a[w] | maj | (one.a[w] & some);
+                    one.a[w] |= some;
+                }
+            }
+#pragma unroll
+            for (int j = DC - DC % 3; j < DC; j++) {   // dc not a multiple of 3: the last one or two sockets
+                const VecT<WORDS> xv = x[s_c2v[j * m_pad + c]];
+                LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < dc; j++) {
+                const int v = s_c2v[j * m_pad + c];
+                const VecT<WORDS> xv = x[v];
+                LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
+                if (VALUES) {
+                    const VecT<WORDS> vv = val[v];  // invariant: value bits are 0 where erased
+                    LDPC_FORW pr.a[w] ^= vv.a[w];
+                }
             }
         }
         two[c] = tw;
