@@ -25,7 +25,7 @@ namespace ldpc {
 
 constexpr int E1_MAX_THREADS = 512;
 // one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
-__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : 512; }
+__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? 768 : 512); }
 
 template <int WORDS> struct VecT;
 template <> struct alignas(4)  VecT<1> { uint32_t a[1]; };

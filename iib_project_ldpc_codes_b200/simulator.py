@@ -13,8 +13,9 @@ Same names, argument meaning and outputs as the reference (file:line relative to
 Out of scope here: the ML decoder (`optimal_decode`, modes 1/2/4/5 raise NotImplementedError).
 
 Differences that follow from batching (documented, not hidden):
-  * the 200-block-error stop rule (:200, :367) is evaluated between batches of frames, so a run can
-    overshoot the 200th failure by at most one batch; `stop_rule_batch` sets the granularity;
+  * the 200-block-error stop rule (:200, :367) is evaluated between batches of frames; in fixed-code mode the
+    batch that crosses the limit is then truncated EXACTLY at the frame of the 200th failure by bisection on the
+    deterministic counters (`exact_stop=True`), in ensemble mode the overshoot is at most `stop_rule_graphs` graphs;
   * ensemble mode draws one fresh graph per FRAME GROUP (`frames_per_graph`, default 128) instead of one
     per frame: the expectation of every statistic over the ensemble is unchanged (frames are exchangeable),
     frames sharing a graph are correlated through the code only;
@@ -120,8 +121,29 @@ def _finish(prefix, eps, n, k, dv, dc, iterations, counters, write_csv):
             "counters": counters}
 
 
+def modified_density_evolution(erasure_prob, iterations, dv, dc):
+    """Expected erased fraction per flooding iteration of the reference's one-state-per-variable decoder
+    (restates tools/density_evolution.py:18-28): the per-variable residual uses all dv checks."""
+    results = [erasure_prob]
+    last = erasure_prob
+    for _ in range(iterations):
+        q = 1.0 - (1.0 - last) ** (dc - 1)
+        results.append(erasure_prob * q ** dv)
+        last = erasure_prob * q ** (dv - 1)
+    return np.array(results)
+
+
+def density_evolution_overlay(average_errors, eps, dv, dc, first=8):
+    """Built-in validation the reference did by eye (tools/plotting.py:86): simulated mean curve vs. modified
+    density evolution over the first iterations (finite-length effects grow later)."""
+    k = min(first, len(average_errors))
+    de = modified_density_evolution(eps, k - 1, dv, dc)
+    dev = np.abs(np.asarray(average_errors[:k], dtype=np.float64) - de)
+    return {"iterations_compared": int(k), "max_abs_deviation": float(dev.max()), "de_curve": de.tolist()}
+
+
 def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=None, stop_rule_batch=None,
-                              wall_clock_limit=42000):
+                              wall_clock_limit=42000, exact_stop=True, max_block_errors=200):
     """Fixed-code Monte-Carlo (parallel_simulator_expurgated.py:287-414)."""
     eps = parameter_set["BEC"]
     num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
@@ -150,12 +172,29 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
     batch = stop_rule_batch or max(4096, min(num_tests, 1 << 22))
     batch = (batch + 127) // 128 * 128
     # :367  while block_error<200 and i<num_tests and elapsed < 42000
-    while int(total[iterations + 1]) < 200 and done < num_tests and time.time() - start < wall_clock_limit:
+    while int(total[iterations + 1]) < max_block_errors and done < num_tests and time.time() - start < wall_clock_limit:
         cnt = min(batch, num_tests - done)
-        total += g.mc_run([eps], seed, cnt, iterations, expurgation=-1, first_frame=done)[0]
+        part = g.mc_run([eps], seed, cnt, iterations, expurgation=-1, first_frame=done)[0]
+        if exact_stop and int(total[iterations + 1]) + int(part[iterations + 1]) >= max_block_errors:
+            # The reference stops right after the frame that brings block_error to 200 (:367).  Frames are
+            # keyed by their index, so the shortest prefix of this batch reaching the limit is found by
+            # bisection on the (deterministic, additive) counters: exact ordered truncation.
+            need = max_block_errors - int(total[iterations + 1])
+            lo, hi = 1, cnt          # smallest L in [1, cnt] with block_errors(done, done+L) >= need
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if int(g.mc_run([eps], seed, mid, iterations, expurgation=-1, first_frame=done)[0][iterations + 1]) >= need:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            cnt = lo
+            part = g.mc_run([eps], seed, cnt, iterations, expurgation=-1, first_frame=done)[0]
+        total += part
         done += cnt
     g.close()
-    return _finish("regular_code_code_number=" + str(filenumber), eps, n, k, dv, dc, iterations, total, write_csv)
+    res = _finish("regular_code_code_number=" + str(filenumber), eps, n, k, dv, dc, iterations, total, write_csv)
+    res["density_evolution"] = density_evolution_overlay(res["average_errors"], eps, dv, dc)
+    return res
 
 
 def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=64,

@@ -110,3 +110,10 @@ def test_generate_random_code_identical_to_reference_given_same_libc_rand_state(
         libc.srand(ct.c_uint(s))
         vm, cm, Hm, _ = _call_generate_random_code(mine, n, dv, dc)
         assert np.array_equal(vr, vm) and np.array_equal(cr, cm) and np.array_equal(Hr, Hm)
+
+
+def test_modified_density_evolution_matches_reference_values():
+    """tools/density_evolution.py:18-28 at eps=0.40, (3,6): 0.4, 0.313756, 0.267938, 0.236467, 0.211673."""
+    from iib_project_ldpc_codes_b200.simulator import modified_density_evolution
+    got = modified_density_evolution(0.40, 4, 3, 6)
+    assert np.allclose(got, [0.4, 0.313756, 0.267938, 0.236467, 0.211673], atol=1e-6)

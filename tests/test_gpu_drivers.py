@@ -55,10 +55,16 @@ def test_run_simulation_fixed_ldpc_counters_csv_and_cache(S, oracle):
     cl = np.load(os.path.join(pdir, "check_code_no_7_n_504_dv_3_dc_6.npy")).reshape(252, 6)
     vl = np.load(os.path.join(pdir, "variable_code_no_7_n_504_dv_3_dc_6.npy")).reshape(504, 3)
     frames = r["num_tests"]
-    assert frames % 1024 == 0 or frames == 3000
     want = oracle.best().mc_run(vl, cl, 504, 252, 3, 6, [0.42], 11, 0, frames, 60, -1, nthreads=8)[0]
     assert np.array_equal(r["counters"], want)
-    assert r["block_errors"] >= 200 or frames == 3000          # stop rule, batch granularity
+    # exact ordered truncation (parallel_simulator_expurgated.py:367): the run ends with the frame of the 200th failure
+    assert r["block_errors"] == 200 and frames < 3000
+    before = oracle.best().mc_run(vl, cl, 504, 252, 3, 6, [0.42], 11, 0, frames - 1, 60, -1, nthreads=8)[0]
+    assert int(before[61]) == 199
+    assert r["density_evolution"]["max_abs_deviation"] < 0.02   # mean curve follows modified DE (tools/plotting.py:86)
+    # batch-granular variant overshoots by less than one batch
+    rb = S.run_simulation_fixed_ldpc(p, stop_rule_batch=1024, run_seed=11, write_csv=False, exact_stop=False)
+    assert rb["block_errors"] >= 200 and rb["num_tests"] % 1024 == 0 and rb["num_tests"] - frames < 1024
     # CSV: iterations+1 rows, then the two labelled rows (parallel_simulator.py:26-32); filename schema
     path = os.path.join(S.base_directory, "report_data", "simulation_data", r["filename"])
     rows = list(csv.reader(open(path)))
