@@ -134,10 +134,29 @@ def run_reference(args, wl):
                              "edge_updates_per_s": eu},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; keep stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -314,7 +333,7 @@ def main():
         line["extra_n1000"] = {"workload": w1["desc"].replace("10^8", "2*10^7"), "frames_per_s_per_gpu": f1 / t1,
                                "edge_updates_per_s_per_gpu": int(c1n[0, w1["cap"] + 5]) * 3000 / t1,
                                "engine": g1.mc_stats()}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         tdist.destroy_process_group()
 

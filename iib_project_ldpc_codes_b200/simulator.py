@@ -218,6 +218,7 @@ def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128
                 break
             vl, cl = api.generate_graph(n, dv, dc, seed=seed * 1000003 + gi, mode=1)
             g = api.Graph(vl, cl, device=device)
+            g.set_place_effort(0)   # a graph lives for one frame group: no time for a placement search
             cnt = min(frames_per_graph, num_tests - done)
             total += g.mc_run([eps], seed, cnt, iterations, expurgation=expurgation, first_frame=gi * frames_per_graph)[0]
             g.close()
