@@ -80,14 +80,25 @@ __device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long 
         const int c = (int)(t / Q), q = (int)(t - (unsigned long long)c * Q);
         uint4 one = make_uint4(0, 0, 0, 0), two = one, par = one;
         const int* idx = P.c2v + (size_t)c * P.dc;
-        for (int j = 0; j < P.dc; j++) {
-            const int v = __ldg(idx + j);
-            const uint4 w = P.X[(size_t)v * Q + q];
-            two.x |= one.x & w.x; two.y |= one.y & w.y; two.z |= one.z & w.z; two.w |= one.w & w.w;
-            one.x |= w.x; one.y |= w.y; one.z |= w.z; one.w |= w.w;
-            if (VALUES) {
-                const uint4 vv = P.V[(size_t)v * Q + q];
-                par.x ^= vv.x; par.y ^= vv.y; par.z ^= vv.z; par.w ^= vv.w;
+        // sockets in batches of 8: all row gathers of a batch are in flight before the first is combined
+        // (memory-level parallelism; a missing socket contributes the neutral word 0)
+        for (int j0 = 0; j0 < P.dc; j0 += 8) {
+            uint4 w[8], vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                w[u] = make_uint4(0, 0, 0, 0);
+                if (VALUES) vv[u] = make_uint4(0, 0, 0, 0);
+                if (j0 + u < P.dc) {
+                    const int v = __ldg(idx + j0 + u);
+                    w[u] = P.X[(size_t)v * Q + q];
+                    if (VALUES) vv[u] = P.V[(size_t)v * Q + q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                two.x |= one.x & w[u].x; two.y |= one.y & w[u].y; two.z |= one.z & w[u].z; two.w |= one.w & w[u].w;
+                one.x |= w[u].x; one.y |= w[u].y; one.z |= w[u].z; one.w |= w[u].w;
+                if (VALUES) { par.x ^= vv[u].x; par.y ^= vv[u].y; par.z ^= vv[u].z; par.w ^= vv[u].w; }
             }
         }
         P.T[t] = two;
@@ -110,14 +121,25 @@ __device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long lo
         const uint4 xi = P.X[t];
         uint4 xn = xi, nv = make_uint4(0, 0, 0, 0);
         const int* idx = P.v2c + (size_t)i * P.dv;
-        for (int j = 0; j < P.dv; j++) {
-            const int c = __ldg(idx + j);
-            const uint4 tw = P.T[(size_t)c * Q + q];
-            xn.x &= tw.x; xn.y &= tw.y; xn.z &= tw.z; xn.w &= tw.w;
-            if (VALUES) {
-                const uint4 pr = P.PAR[(size_t)c * Q + q];
-                nv.x = (nv.x & tw.x) | (pr.x & ~tw.x); nv.y = (nv.y & tw.y) | (pr.y & ~tw.y);
-                nv.z = (nv.z & tw.z) | (pr.z & ~tw.z); nv.w = (nv.w & tw.w) | (pr.w & ~tw.w);
+        for (int j0 = 0; j0 < P.dv; j0 += 4) {   // batches of 4 gathers in flight; neutral word = all ones
+            uint4 tw[4], pr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                tw[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (VALUES) pr[u] = make_uint4(0, 0, 0, 0);
+                if (j0 + u < P.dv) {
+                    const int c = __ldg(idx + j0 + u);
+                    tw[u] = P.T[(size_t)c * Q + q];
+                    if (VALUES) pr[u] = P.PAR[(size_t)c * Q + q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                xn.x &= tw[u].x; xn.y &= tw[u].y; xn.z &= tw[u].z; xn.w &= tw[u].w;
+                if (VALUES) {   // listed order, last writer wins (message_passing.c:56-61)
+                    nv.x = (nv.x & tw[u].x) | (pr[u].x & ~tw[u].x); nv.y = (nv.y & tw[u].y) | (pr[u].y & ~tw[u].y);
+                    nv.z = (nv.z & tw[u].z) | (pr[u].z & ~tw[u].z); nv.w = (nv.w & tw[u].w) | (pr[u].w & ~tw[u].w);
+                }
             }
         }
         if (xn.x != xi.x || xn.y != xi.y || xn.z != xi.z || xn.w != xi.w) {
