@@ -191,7 +191,7 @@ __device__ __forceinline__ void e2_count_phase(const E2Params& P, unsigned long 
 }
 
 template <bool VALUES, bool DECODE>
-__global__ void __launch_bounds__(E2_THREADS) e2_kernel(const __grid_constant__ E2Params P) {
+__global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant__ E2Params P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t s_or[2 * E2_RMAX];
     __shared__ uint32_t s_cnt;
