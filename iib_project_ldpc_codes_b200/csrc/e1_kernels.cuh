@@ -192,7 +192,9 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
         }
         bool changed = false;
         LDPC_FORW changed |= (xn.a[w] != xi.a[w]);
-        if (changed) {
+        if (!VALUES) {
+            x[i] = xn;   // unconditional: a predicated store costs more issue slots than the store saves
+        } else if (changed) {
             x[i] = xn;
             if (VALUES) {
                 VecT<WORDS> vi = val[i];
