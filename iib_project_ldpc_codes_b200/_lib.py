@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libldpc_b200.so")
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(PKG_DIR, "libldpc_b200.so")
 
 P_I32 = ct.POINTER(ct.c_int)
 P_I8 = ct.POINTER(ct.c_int8)

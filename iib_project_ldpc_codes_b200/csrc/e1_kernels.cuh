@@ -24,6 +24,16 @@
 namespace ldpc {
 
 constexpr int E1_MAX_THREADS = 512;
+#ifndef LDPC_CHECK_UNROLL
+#define LDPC_CHECK_UNROLL 1
+#endif
+#ifndef LDPC_VAR_UNROLL
+#define LDPC_VAR_UNROLL 2
+#endif
+#ifndef LDPC_VAR_UNROLL_VG
+#define LDPC_VAR_UNROLL_VG 4
+#endif
+constexpr int kCheckUnroll = LDPC_CHECK_UNROLL, kVarUnroll = LDPC_VAR_UNROLL, kVarUnrollVG = LDPC_VAR_UNROLL_VG;
 // one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
 __host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? 768 : 512); }
 
@@ -118,7 +128,7 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
                                             const VecT<WORDS>* __restrict__ val, VecT<WORDS>* __restrict__ par) {
     const int dc = DC ? DC : P.dc;
     const int m = P.m, m_pad = P.m_pad;
-#pragma unroll 2
+#pragma unroll kCheckUnroll
     for (int c = t.tid; c < m; c += t.nthr) {
         VecT<WORDS> one, tw, pr;
         LDPC_FORW { one.a[w] = 0u; tw.a[w] = 0u; pr.a[w] = 0u; }
@@ -175,7 +185,7 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
     const int n = P.n, n_pad = P.n_pad;
     LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
     cnt = 0u;
-#pragma unroll(VG ? 4 : 2)
+#pragma unroll(VG ? kVarUnrollVG : kVarUnroll)
     for (int i = t.tid; i < n; i += t.nthr) {
         const VecT<WORDS> xi = x[i];
         VecT<WORDS> xn = xi, nv;
