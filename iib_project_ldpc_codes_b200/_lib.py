@@ -42,7 +42,7 @@ EXPORTS = [
     "ldpc_b200_generate_graph", "ldpc_b200_graph_create", "ldpc_b200_graph_destroy", "ldpc_b200_counters_len",
     "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
     "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning", "ldpc_b200_smem_probe",
-    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine",
+    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble",
 ]
 
 _lib = None
@@ -77,6 +77,10 @@ def load() -> ct.CDLL:
     lib.ldpc_b200_mc_run.restype = ct.c_int
     lib.ldpc_b200_mc_run.argtypes = [ct.c_void_p, P_F64, ct.c_int, ct.c_uint64, ct.c_uint64, ct.c_uint64, ct.c_int,
                                      ct.c_int, P_U64, ct.POINTER(McStats)]
+    lib.ldpc_b200_mc_run_ensemble.restype = ct.c_int
+    lib.ldpc_b200_mc_run_ensemble.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_uint64, ct.c_int, ct.c_uint64,
+                                              ct.c_uint64, ct.c_uint32, P_F64, ct.c_int, ct.c_uint64, ct.c_int, ct.c_int,
+                                              P_U64, ct.POINTER(McStats)]
     lib.ldpc_b200_mc_launch.restype = ct.c_int
     lib.ldpc_b200_mc_launch.argtypes = [ct.c_void_p, P_F64, ct.c_int, ct.c_uint64, ct.c_uint64, ct.c_uint64, ct.c_int,
                                         ct.c_int, ct.c_void_p, ct.c_void_p]

@@ -61,6 +61,14 @@ struct E1Params {
     // geometry
     int team_warps, teams;
     int v2c_global;   // 1: variable-side lookups stay in global memory (not staged into shared memory)
+    // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
+    // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
+    // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c
+    int ens;
+    unsigned long long ens_stride_c, ens_stride_v;   // uint16 elements per graph
+    unsigned long long ens_gpg;                      // frame groups per graph
+    unsigned long long ens_wpg;                      // 32-frame words between the first frames of consecutive graphs
+    unsigned long long ens_fpg;                      // frames per graph
     // shared-memory byte offsets
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride;
     uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
 
     // stage the graph once per CTA (16-byte vectors; arrays are padded to 16 bytes on the host)
-    {
+    if (!P.ens) {
         const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
         const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
         const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
@@ -316,6 +324,11 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     const unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
     const int W = 32 * WORDS;
     const int stride = raw_stride(P.cap);
+    if (P.ens) {
+        s_c2v = reinterpret_cast<uint16_t*>(base + P.sm_c2v);
+        s_v2c = reinterpret_cast<uint16_t*>(base + P.sm_v2c);
+    }
+    long long staged_graph = -1;
 
     for (;;) {
         // ---- fetch a work item (point, group) ----
@@ -335,14 +348,36 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         if (item >= total) break;
         const uint32_t point = (uint32_t)(item / P.groups_per_point);
         const unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
-        const unsigned long long q0 = P.first_word + gi * WORDS;
+        unsigned long long q0 = P.first_word + gi * WORDS;
         const BecParams bp = P.bec[point];
 
         uint32_t valid[WORDS];
-        LDPC_FORW {
-            const unsigned long long f0 = (gi * WORDS + w) * 32ull;  // first frame of this word, relative
-            valid[w] = f0 >= P.num_frames ? 0u
-                       : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+        if (!P.ens) {
+            LDPC_FORW {
+                const unsigned long long f0 = (gi * WORDS + w) * 32ull;  // first frame of this word, relative
+                valid[w] = f0 >= P.num_frames ? 0u
+                           : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+            }
+        } else {
+            const unsigned long long g = gi / P.ens_gpg, gg = gi - g * P.ens_gpg;
+            if ((long long)g != staged_graph) {   // the previous group of this team ended with a team_sync
+                const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
+                const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
+                const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v + g * P.ens_stride_c);
+                const uint4* g1 = reinterpret_cast<const uint4*>(P.v2c + g * P.ens_stride_v);
+                uint4* d0 = reinterpret_cast<uint4*>(s_c2v);
+                uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
+                for (int i = t.tid; i < nc; i += t.nthr) d0[i] = __ldg(g0 + i);
+                for (int i = t.tid; i < nv; i += t.nthr) d1[i] = __ldg(g1 + i);
+                team_sync(t);
+                staged_graph = (long long)g;
+            }
+            q0 = P.first_word + g * P.ens_wpg + gg * WORDS;
+            LDPC_FORW {
+                const unsigned long long f0 = (gg * WORDS + w) * 32ull;
+                valid[w] = f0 >= P.ens_fpg ? 0u
+                           : (P.ens_fpg - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.ens_fpg - f0)) - 1u));
+            }
         }
 
         uint32_t any[WORDS], cnt;

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <mutex>
+#include <atomic>
 #include <string>
 #include <vector>
 #include <unordered_map>
@@ -485,6 +486,8 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     g->last.grid = grid_used; g->last.smem_bytes = (int)cfg.smem;
     return LDPC_B200_OK;
 }
+
+#include "e1_ens_host.inc"
 
 extern "C" int ldpc_b200_mc_stats_read(ldpc_b200_graph* g, ldpc_b200_mc_stats* stats) {
     if (!g || !stats) return fail(LDPC_B200_EINVAL, "mc_stats_read: NULL argument");

@@ -197,9 +197,13 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
     return res
 
 
-def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=64,
-                   wall_clock_limit=43000):
-    """Ensemble Monte-Carlo (parallel_simulator_expurgated.py:169-285): a fresh random graph per frame group."""
+def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=4096,
+                   wall_clock_limit=43000, gen_mode=1):
+    """Ensemble Monte-Carlo (parallel_simulator_expurgated.py:169-285): a fresh random graph per frame group.
+
+    Graph G of the run is generate_graph(n, dv, dc, seed*1000003 + G, gen_mode) and decodes the global frames
+    [G*F, G*F + frames_per_graph), F = frames_per_graph rounded up to 128 (ldpc_b200_mc_run_ensemble); the
+    200-block-error rule (:200) is checked every `stop_rule_graphs` graphs."""
     eps = parameter_set["BEC"]
     num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
     n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]
@@ -209,22 +213,19 @@ def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128
     expurgation = int(parameter_set.get("expurgation", -1))
     k = int(n * (dc - dv) / dc)
     start = time.time()
-    frames_per_graph = (frames_per_graph + 127) // 128 * 128
     total = np.zeros(iterations + 6, dtype=np.uint64)
     done, gi = 0, 0
     while int(total[iterations + 1]) < 200 and done < num_tests and time.time() - start < wall_clock_limit:   # :200
-        for _ in range(stop_rule_graphs):
-            if done >= num_tests:
-                break
-            vl, cl = api.generate_graph(n, dv, dc, seed=seed * 1000003 + gi, mode=1)
-            g = api.Graph(vl, cl, device=device)
-            g.set_place_effort(0)   # a graph lives for one frame group: no time for a placement search
-            cnt = min(frames_per_graph, num_tests - done)
-            total += g.mc_run([eps], seed, cnt, iterations, expurgation=expurgation, first_frame=gi * frames_per_graph)[0]
-            g.close()
-            done += cnt
-            gi += 1
-    return _finish("regular_code_expurgated=" + str(expurgation), eps, n, k, dv, dc, iterations, total, write_csv)
+        # whole graphs only: num_tests is rounded up to a multiple of frames_per_graph (the CSV reports the actual count)
+        graphs = min(stop_rule_graphs, (num_tests - done + frames_per_graph - 1) // frames_per_graph)
+        total += api.mc_run_ensemble(n, dv, dc, [eps], seed, graphs, iterations, frames_per_graph=frames_per_graph,
+                                     graph_seed=seed, gen_mode=gen_mode, first_graph=gi, expurgation=expurgation,
+                                     device=device)[0]
+        done += graphs * frames_per_graph
+        gi += graphs
+    res = _finish("regular_code_expurgated=" + str(expurgation), eps, n, k, dv, dc, iterations, total, write_csv)
+    res["graphs"] = gi
+    return res
 
 
 def main(argv=None):

@@ -79,19 +79,41 @@ def test_run_simulation_fixed_ldpc_counters_csv_and_cache(S, oracle):
     assert np.array_equal(r2["counters"], r["counters"])
 
 
+def _ensemble_reference(oracle, L, n, dv, dc, eps, seed, graph_seed, first_graph, graphs, fpg, its, exp, gen_mode=1):
+    F = (fpg + 127) // 128 * 128
+    want = np.zeros((len(eps), its + 6), dtype=np.uint64)
+    for g in range(first_graph, first_graph + graphs):
+        vl, cl = L.generate_graph(n, dv, dc, seed=graph_seed * 1000003 + g, mode=gen_mode)
+        want += oracle.best().mc_run(vl, cl, n, n - n * dv // dc, dv, dc, eps, seed, g * F, fpg, its, exp, nthreads=4)
+    return want
+
+
+@pytest.mark.parametrize("n,dv,dc,fpg,graphs,exp", [(240, 3, 6, 128, 9, 0), (240, 3, 6, 128, 9, -1), (504, 3, 6, 100, 5, 3),
+                                                     (1000, 3, 6, 300, 4, -1), (2000, 4, 8, 128, 6, 0), (96, 3, 6, 32, 40, -1)])
+def test_mc_run_ensemble_matches_reference_per_graph(S, oracle, n, dv, dc, fpg, graphs, exp):
+    """Fresh graph per frame group (parallel_simulator_expurgated.py:200-243): the counters equal the reference frame
+    loop run graph by graph on the same graphs and erasure patterns."""
+    import iib_project_ldpc_codes_b200 as L
+    eps, seed, gseed, its = [0.36, 0.42], 77, 5, 60
+    got, st = L.mc_run_ensemble(n, dv, dc, eps, seed, graphs, its, frames_per_graph=fpg, graph_seed=gseed, first_graph=3,
+                                expurgation=exp, return_stats=True)
+    want = _ensemble_reference(oracle, L, n, dv, dc, eps, seed, gseed, 3, graphs, fpg, its, exp)
+    assert np.array_equal(got, want)
+    # additive over graph ranges
+    a = L.mc_run_ensemble(n, dv, dc, eps, seed, 2, its, frames_per_graph=fpg, graph_seed=gseed, first_graph=3, expurgation=exp)
+    b = L.mc_run_ensemble(n, dv, dc, eps, seed, graphs - 2, its, frames_per_graph=fpg, graph_seed=gseed, first_graph=5,
+                          expurgation=exp)
+    assert np.array_equal(a + b, got)
+
+
 def test_run_simulation_ensemble_expurgated(S, oracle):
     import iib_project_ldpc_codes_b200 as L
     p = {"BEC": 0.40, "expurgation": 0, "num_tests": 1000, "iterations": 40, "n": 240, "dv": 3, "dc": 6,
          "optimal": False, "message_passing": True, "seed": 3}
     r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4)
-    # rebuild the same graphs and feed the reference frame loop the same frames
-    want = np.zeros(46, dtype=np.uint64)
-    graphs = (r["num_tests"] + 127) // 128
-    left = r["num_tests"]
-    for gi in range(graphs):
-        vl, cl = L.generate_graph(240, 3, 6, seed=3 * 1000003 + gi, mode=1)
-        cnt = min(128, left); left -= cnt
-        want += oracle.best().mc_run(vl, cl, 240, 120, 3, 6, [0.40], 3, gi * 128, cnt, 40, 0, nthreads=2)[0]
+    graphs = r["graphs"]
+    assert r["num_tests"] == graphs * 128 and r["num_tests"] >= 1000      # whole graphs, rounded up
+    want = _ensemble_reference(oracle, L, 240, 3, 6, [0.40], 3, 3, 0, graphs, 128, 40, 0)[0]
     assert np.array_equal(r["counters"], want)
     assert "regular_code_expurgated=0_BEC=0.4_n=240" in r["filename"]
 
