@@ -49,18 +49,18 @@ __device__ __forceinline__ uint32_t bec_word(const BecParams& bp, uint32_t point
         uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
         philox4x32_10(r0, r1, r2, r3, bp.seed_lo, bp.seed_hi);
         const uint32_t r[4] = {r0, r1, r2, r3};
-        bool done = false;
+        // Four levels without branches: m = all-ones iff the threshold bit of the level is set (warp-uniform).
+        //   bit set:   lt |= eq & ~r ; eq &= r        bit clear:   eq &= ~r
+        // Levels past the point where every frame is decided (eq == 0) or where no lower threshold bit is
+        // set cannot change lt, so the exit tests only need to run once per block.
+        const uint32_t tb = t << (4 * b);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            if (!done) {
-                const int j = 4 * b + s;
-                if ((t >> (31 - j)) & 1u) { lt |= eq & ~r[s]; eq &= r[s]; }
-                else                      { eq &= ~r[s]; }
-                // decided everywhere, or no set bit of T below this level
-                if (eq == 0u || j == 31 || (t << (j + 1)) == 0u) done = true;
-            }
+            const uint32_t m = (uint32_t)((int32_t)(tb << s) >> 31);
+            lt |= eq & ~r[s] & m;
+            eq &= ~(r[s] ^ m);
         }
-        if (done) break;
+        if (eq == 0u || b == 7 || (t << (4 * b + 4)) == 0u) break;
     }
     return lt;
 }

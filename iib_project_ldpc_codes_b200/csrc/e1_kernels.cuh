@@ -24,6 +24,9 @@
 namespace ldpc {
 
 constexpr int E1_MAX_THREADS = 512;
+#ifndef LDPC_W64_THREADS
+#define LDPC_W64_THREADS 512
+#endif
 #ifndef LDPC_CHECK_UNROLL
 #define LDPC_CHECK_UNROLL 1
 #endif
@@ -35,7 +38,7 @@ constexpr int E1_MAX_THREADS = 512;
 #endif
 constexpr int kCheckUnroll = LDPC_CHECK_UNROLL, kVarUnroll = LDPC_VAR_UNROLL, kVarUnrollVG = LDPC_VAR_UNROLL_VG;
 // one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
-__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? 768 : 512); }
+__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? 768 : LDPC_W64_THREADS); }
 
 template <int WORDS> struct VecT;
 template <> struct alignas(4)  VecT<1> { uint32_t a[1]; };
