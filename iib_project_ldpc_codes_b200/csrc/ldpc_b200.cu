@@ -94,6 +94,9 @@ struct ldpc_b200_graph {
     void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0;
     unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
     int* d_cuts = nullptr; size_t cuts_cap = 0;
+    // batched decode buffers (cached between calls)
+    void* dec_mvc = nullptr; void* dec_x = nullptr; void* dec_v = nullptr; void* dec_err = nullptr; void* dec_ret = nullptr;
+    size_t dec_mvc_cap = 0, dec_x_cap = 0, dec_v_cap = 0, dec_err_cap = 0, dec_ret_cap = 0;
     int launches = 0;      // kernels launched since the last stats read
     int last_stages = 1;
     // workspace
@@ -256,6 +259,7 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
     cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
     cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_cuts);
+    cudaFree(g->dec_mvc); cudaFree(g->dec_x); cudaFree(g->dec_v); cudaFree(g->dec_err); cudaFree(g->dec_ret);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
 }
@@ -552,65 +556,93 @@ static cudaError_t launch_decode(const E1Params& P, int grid, int block, uint32_
     return go(e1_decode_kernel<0, 0, VALUES>);
 }
 
+// flags |= 1 if some symbol == 1 (value plane needed), |= 2 if some symbol is outside {0,1,2}
+__global__ void scan_symbols_kernel(const int8_t* __restrict__ mvc, size_t total, unsigned int* flags) {
+    unsigned int f = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int8_t s = mvc[i];
+        f |= (s == 1) ? 1u : 0u;
+        f |= (s < 0 || s > 2) ? 2u : 0u;
+    }
+    f = __reduce_or_sync(0xFFFFFFFFu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+static int grow(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return LDPC_B200_OK;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return LDPC_B200_OK;
+}
+
 extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
                                       int* errors, int* ret) {
     if (!g || !Mvc || !ret || (!errors && iterations > 0)) return fail(LDPC_B200_EINVAL, "decode_batch: NULL argument");
     if (iterations < 0) return fail(LDPC_B200_EINVAL, "decode_batch: iterations < 0");
     if (frames == 0) return LDPC_B200_OK;
     CUDA_TRY(cudaSetDevice(g->device));
-    const size_t total = (size_t)frames * g->n;
-    bool values = false;
-    for (size_t i = 0; i < total; i++) {
-        const int8_t s = Mvc[i];
-        if (s < 0 || s > 2) return fail(LDPC_B200_EINVAL, "decode_batch: symbol %d at frame %zu position %zu is outside {0,1,2}", (int)s, i / g->n, i % g->n);
-        values |= (s == 1);
-    }
-    E1Config cfg;
+    // chunks of at most 2^20 frames (device buffers are cached in the handle and reused)
+    const uint64_t chunk_frames = std::min<uint64_t>(frames, std::max<uint64_t>(1024, std::min<uint64_t>(1ull << 20, (1ull << 31) / (uint64_t)std::max(g->n, 1))));
+    const size_t cb = (size_t)chunk_frames * g->n;
+    const uint64_t cgroups = (chunk_frames + 31) / 32;
+    int rc;
+    if ((rc = grow(&g->dec_mvc, &g->dec_mvc_cap, cb))) return rc;
+    if ((rc = grow(&g->dec_x, &g->dec_x_cap, cgroups * g->n * 4))) return rc;
+    if ((rc = grow(&g->dec_v, &g->dec_v_cap, cgroups * g->n * 4))) return rc;
+    if ((rc = grow(&g->dec_err, &g->dec_err_cap, (size_t)chunk_frames * std::max(iterations, 1) * 4))) return rc;
+    if ((rc = grow(&g->dec_ret, &g->dec_ret_cap, (size_t)chunk_frames * 4 + 16))) return rc;
+    unsigned int* d_flags = (unsigned int*)((char*)g->dec_ret + (size_t)chunk_frames * 4);
     const int weng = want_engine(g);
-    const bool fits_e1 = plan_e1(g, iterations, values, true, cfg);
-    if (weng == 1 && !fits_e1)
-        return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: graph (n=%d dv=%d dc=%d, value plane %s) does not fit the shared-memory engine",
-                    g->n, g->dv, g->dc, values ? "on" : "off");
-    const uint64_t groups = (frames + 31) / 32;
-    DevBuf d_mvc, d_x, d_v, d_err, d_ret;
-    if (weng == 2 || !fits_e1) {
-        CUDA_TRY(d_mvc.alloc(total));
-        CUDA_TRY(d_err.alloc((size_t)frames * iterations * 4));
-        CUDA_TRY(d_ret.alloc((size_t)frames * 4));
-        CUDA_TRY(cudaMemcpy(d_mvc.p, Mvc, total, cudaMemcpyHostToDevice));
-        int rc2 = e2_decode(g, (int8_t*)d_mvc.p, frames, iterations, values, (int*)d_err.p, (int*)d_ret.p);
-        if (rc2) return rc2;
-        CUDA_TRY(cudaMemcpy(Mvc, d_mvc.p, total, cudaMemcpyDeviceToHost));
-        if (iterations > 0) CUDA_TRY(cudaMemcpy(errors, d_err.p, (size_t)frames * iterations * 4, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(ret, d_ret.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
-        return LDPC_B200_OK;
-    }
-    CUDA_TRY(d_mvc.alloc(total));
-    CUDA_TRY(d_x.alloc(groups * g->n * 4));
-    CUDA_TRY(d_v.alloc(groups * g->n * 4));
-    CUDA_TRY(d_err.alloc((size_t)frames * iterations * 4));
-    CUDA_TRY(d_ret.alloc((size_t)frames * 4));
-    CUDA_TRY(cudaMemcpy(d_mvc.p, Mvc, total, cudaMemcpyHostToDevice));
-    dim3 pgrid((g->n + 127) / 128, (unsigned)groups);
-    if (groups > 65535) return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: more than 65535*32 frames per call");
-    pack_planes_kernel<<<pgrid, 128>>>((const int8_t*)d_mvc.p, (uint32_t*)d_x.p, (uint32_t*)d_v.p, frames, g->n);
-    CUDA_TRY(cudaGetLastError());
 
-    E1Params P;
-    fill_params(g, cfg, iterations, P);
-    P.num_frames = frames; P.groups_per_point = groups;
-    P.xin = (const uint32_t*)d_x.p; P.vin = (const uint32_t*)d_v.p;
-    P.xout = (uint32_t*)d_x.p; P.vout = (uint32_t*)d_v.p;
-    P.errors = (int*)d_err.p; P.ret = (int*)d_ret.p;
-    const int grid = (int)std::min<uint64_t>((uint64_t)g->sm_count, (groups + cfg.teams - 1) / cfg.teams);
-    const int block = cfg.teams * cfg.team_warps * 32;
-    cudaError_t e = values ? launch_decode<true>(P, grid, block, cfg.smem, 0) : launch_decode<false>(P, grid, block, cfg.smem, 0);
-    if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "decode_batch: kernel launch failed: %s", cudaGetErrorString(e));
-    unpack_planes_kernel<<<pgrid, 128>>>((int8_t*)d_mvc.p, (const uint32_t*)d_x.p, (const uint32_t*)d_v.p, frames, g->n);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(Mvc, d_mvc.p, total, cudaMemcpyDeviceToHost));
-    if (iterations > 0) CUDA_TRY(cudaMemcpy(errors, d_err.p, (size_t)frames * iterations * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(ret, d_ret.p, (size_t)frames * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t f0 = 0; f0 < frames; f0 += chunk_frames) {
+        const uint64_t fc = std::min<uint64_t>(chunk_frames, frames - f0);
+        const size_t total = (size_t)fc * g->n;
+        int8_t* hM = Mvc + (size_t)f0 * g->n;
+        CUDA_TRY(cudaMemcpy(g->dec_mvc, hM, total, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, 4, 0));
+        scan_symbols_kernel<<<g->sm_count * 8, 256>>>((const int8_t*)g->dec_mvc, total, d_flags);
+        unsigned int flags = 0;
+        CUDA_TRY(cudaMemcpy(&flags, d_flags, 4, cudaMemcpyDeviceToHost));
+        if (flags & 2u) {
+            for (size_t i = 0; i < total; i++)
+                if (hM[i] < 0 || hM[i] > 2)
+                    return fail(LDPC_B200_EINVAL, "decode_batch: symbol %d at frame %zu position %zu is outside {0,1,2}",
+                                (int)hM[i], (size_t)f0 + i / g->n, i % g->n);
+        }
+        const bool values = (flags & 1u) != 0;
+        E1Config cfg;
+        const bool fits_e1 = plan_e1(g, iterations, values, true, cfg);
+        if (weng == 1 && !fits_e1)
+            return fail(LDPC_B200_EUNSUPPORTED, "decode_batch: graph (n=%d dv=%d dc=%d, value plane %s) does not fit the shared-memory engine",
+                        g->n, g->dv, g->dc, values ? "on" : "off");
+        int* d_err = (int*)g->dec_err;
+        int* d_ret = (int*)g->dec_ret;
+        if (weng == 2 || !fits_e1) {
+            rc = e2_decode(g, (int8_t*)g->dec_mvc, fc, iterations, values, d_err, d_ret);
+            if (rc) return rc;
+        } else {
+            const uint64_t groups = (fc + 31) / 32;
+            dim3 pgrid((g->n + 127) / 128, (unsigned)groups);
+            pack_planes_kernel<<<pgrid, 128>>>((const int8_t*)g->dec_mvc, (uint32_t*)g->dec_x, (uint32_t*)g->dec_v, fc, g->n);
+            CUDA_TRY(cudaGetLastError());
+            E1Params P;
+            fill_params(g, cfg, iterations, P);
+            P.num_frames = fc; P.groups_per_point = groups;
+            P.xin = (const uint32_t*)g->dec_x; P.vin = (const uint32_t*)g->dec_v;
+            P.xout = (uint32_t*)g->dec_x; P.vout = (uint32_t*)g->dec_v;
+            P.errors = d_err; P.ret = d_ret;
+            const int grid = (int)std::min<uint64_t>((uint64_t)g->sm_count, (groups + cfg.teams - 1) / cfg.teams);
+            const int block = cfg.teams * cfg.team_warps * 32;
+            cudaError_t e = values ? launch_decode<true>(P, grid, block, cfg.smem, 0) : launch_decode<false>(P, grid, block, cfg.smem, 0);
+            if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "decode_batch: kernel launch failed: %s", cudaGetErrorString(e));
+            unpack_planes_kernel<<<pgrid, 128>>>((int8_t*)g->dec_mvc, (const uint32_t*)g->dec_x, (const uint32_t*)g->dec_v, fc, g->n);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpy(hM, g->dec_mvc, total, cudaMemcpyDeviceToHost));
+        if (iterations > 0) CUDA_TRY(cudaMemcpy(errors + (size_t)f0 * iterations, d_err, (size_t)fc * iterations * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ret + f0, d_ret, (size_t)fc * 4, cudaMemcpyDeviceToHost));
+    }
     return LDPC_B200_OK;
 }
 
