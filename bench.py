@@ -332,6 +332,8 @@ def main():
         c1n = d1.cpu().numpy().view(np.uint64)
         line["extra_n1000"] = {"workload": w1["desc"].replace("10^8", "2*10^7"), "frames_per_s_per_gpu": f1 / t1,
                                "edge_updates_per_s_per_gpu": int(c1n[0, w1["cap"] + 5]) * 3000 / t1,
+                               "roofline_frac_smem": int(c1n[0, w1["cap"] + 5]) * 3000 / t1 *
+                               alg_bytes_per_edge_update(3, 6, 1000) / 1e9 / smem_peak,
                                "engine": g1.mc_stats()}
     _emit(line)
     if world > 1:
