@@ -25,7 +25,7 @@ namespace ldpc {
 
 constexpr int E1_MAX_THREADS = 512;
 #ifndef LDPC_W64_THREADS
-#define LDPC_W64_THREADS 512
+#define LDPC_W64_THREADS 768
 #endif
 #ifndef LDPC_CHECK_UNROLL
 #define LDPC_CHECK_UNROLL 1
