@@ -4,9 +4,9 @@ Tanner graphs behind the reference's own C ABI (message_passing.c:7) plus batche
 
 GPU-only: the CUDA library must be built (``__graft_entry__.build()``); there is no CPU fallback.
 """
-from .api import (Graph, McResult, counters_len, draw_patterns, generate_graph, mc_run_ensemble,  # noqa: F401
+from .api import (Graph, McResult, counters_len, draw_patterns, generate_graph, generate_graph_indexed, mc_run_ensemble,  # noqa: F401
                   message_passing)
 from ._lib import LdpcB200Error, LIB_PATH  # noqa: F401
 
-__all__ = ["Graph", "McResult", "counters_len", "draw_patterns", "generate_graph", "mc_run_ensemble", "message_passing",
+__all__ = ["Graph", "McResult", "counters_len", "draw_patterns", "generate_graph", "generate_graph_indexed", "mc_run_ensemble", "message_passing",
            "LdpcB200Error", "LIB_PATH"]

@@ -42,7 +42,7 @@ EXPORTS = [
     "ldpc_b200_generate_graph", "ldpc_b200_graph_create", "ldpc_b200_graph_destroy", "ldpc_b200_counters_len",
     "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
     "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning", "ldpc_b200_smem_probe",
-    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble",
+    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble", "ldpc_b200_generate_graph_indexed",
 ]
 
 _lib = None
@@ -69,6 +69,8 @@ def load() -> ct.CDLL:
                                          ct.c_int, ct.c_bool, ct.c_int]
     lib.ldpc_b200_generate_graph.restype = ct.c_int
     lib.ldpc_b200_generate_graph.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_uint64, ct.c_int, P_I32, P_I32]
+    lib.ldpc_b200_generate_graph_indexed.restype = ct.c_int
+    lib.ldpc_b200_generate_graph_indexed.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_uint64, ct.c_uint64, P_I32, P_I32]
     lib.ldpc_b200_graph_create.restype = ct.c_int
     lib.ldpc_b200_graph_create.argtypes = [P_I32, P_I32, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
                                            ct.POINTER(ct.c_void_p)]

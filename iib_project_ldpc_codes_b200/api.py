@@ -78,6 +78,16 @@ def generate_graph(n: int, dv: int, dc: int, seed: int = 1, mode: int = 1):
     return vl.reshape(n, dv), cl.reshape(n * dv // dc, dc)
 
 
+def generate_graph_indexed(n: int, dv: int, dc: int, graph_seed: int, index: int):
+    """Host twin of the in-kernel ensemble generator (gen_mode 2): graph `index` for `graph_seed`."""
+    lib = _lib.load()
+    vl = np.zeros(n * dv, dtype=np.int32)
+    cl = np.zeros(n * dv, dtype=np.int32)
+    if lib.ldpc_b200_generate_graph_indexed(n, dv, dc, graph_seed, index, ptr(vl, P_I32), ptr(cl, P_I32)) != 1:
+        raise RuntimeError(f"indexed graph generation failed for n={n} dv={dv} dc={dc}")
+    return vl.reshape(n, dv), cl.reshape(n * dv // dc, dc)
+
+
 class Graph:
     """Device-resident Tanner graph (variable_to_check_list [n][dv], check_to_variable_list [m][dc])."""
 

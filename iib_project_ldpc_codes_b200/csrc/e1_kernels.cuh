@@ -55,6 +55,14 @@ template <> struct alignas(16) VecT<4> { uint32_t a[4]; };
 //   [2cap+9]              groups that needed the masked second pass (expurgation)
 __host__ __device__ inline int raw_stride(int cap) { return 2 * cap + 10; }
 
+struct GraphGenParams {
+    uint32_t seed_lo, seed_hi;      // graph seed
+    unsigned long long first_graph; // global index of graph 0 of this launch
+    int epad;                       // n*dv rounded up to a power of two
+    uint32_t sm_keys, sm_vals, sm_fill, sm_conf;   // byte offsets relative to the team base (alias the state region)
+    unsigned long long* fail_flag;  // incremented if a graph could not be generated
+};
+
 struct E1Params {
     // graph (global memory, socket-major uint16: idx[j * pad + node])
     const uint16_t* c2v;
@@ -72,6 +80,7 @@ struct E1Params {
     unsigned long long ens_gpg;                      // frame groups per graph
     unsigned long long ens_wpg;                      // 32-frame words between the first frames of consecutive graphs
     unsigned long long ens_fpg;                      // frames per graph
+    GraphGenParams gg;                               // ens == 2: graphs are generated in the kernel (e1_graphgen.cuh)
     // shared-memory byte offsets
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride;
     uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
@@ -131,6 +140,10 @@ __device__ __forceinline__ void team_reduce(const TeamCtx& t, uint32_t (&ors)[NO
     uint32_t s = have ? t.scr[t.lane * (NOR + 1) + NOR] : 0u;
     sum = __reduce_add_sync(0xFFFFFFFFu, s);
 }
+
+}  // namespace ldpc
+#include "e1_graphgen.cuh"
+namespace ldpc {
 
 // ---- check phase:  two[c] = [>= 2 erased sockets]  (message_passing.c:24-45 collapsed) ----
 template <int WORDS, int DV, int DC, bool VALUES>
@@ -363,7 +376,15 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
             }
         } else {
             const unsigned long long g = gi / P.ens_gpg, gg = gi - g * P.ens_gpg;
-            if ((long long)g != staged_graph) {   // the previous group of this team ended with a team_sync
+            if ((long long)g != staged_graph && P.ens == 2) {
+                // in-kernel generator (e1_graphgen.cuh); its scratch aliases the state region, free between groups
+                if (!team_generate_graph<DV, DC>(P, P.gg, t, base, P.gg.first_graph + g, s_c2v, s_v2c)) {
+                    if (t.tid == 0) atomicAdd(P.gg.fail_flag, 1ull);
+                    team_sync(t);
+                    continue;
+                }
+                staged_graph = (long long)g;
+            } else if ((long long)g != staged_graph) {   // the previous group of this team ended with a team_sync
                 const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
                 const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
                 const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v + g * P.ens_stride_c);

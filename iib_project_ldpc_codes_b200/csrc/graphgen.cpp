@@ -10,6 +10,8 @@
 #include <string.h>
 #include <time.h>
 #include <vector>
+#include <algorithm>
+#include <utility>
 
 #include "../../include/ldpc_b200.h"
 
@@ -57,6 +59,63 @@ struct SplitMix64 {
         return (uint32_t)(mres >> 32);
     }
 };
+
+// Philox4x32-10 (host twin of bec_rng.cuh)
+void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int round = 0; round < 10; round++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// Host twin of the in-kernel generator (e1_graphgen.cuh): keys -> sort -> listed repeats repaired in
+// ascending order with Philox-drawn swap partners.  `seed` = graph seed, `G` = graph index.
+int generate_device_compatible(int n, int dv, int dc, uint64_t seed, uint64_t G, int* check_lookup) {
+    const int E = n * dv, m = E / dc;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), g_lo = (uint32_t)G, g_hi = (uint32_t)(G >> 32);
+    std::vector<std::pair<uint32_t, int>> ks((size_t)E);
+    for (int b = 0; 4 * b < E; b++) {
+        uint32_t r[4] = {(uint32_t)b, g_lo, g_hi, 0x47524148u};
+        philox4x32_10(r, k0, k1);
+        for (int k = 0; k < 4 && 4 * b + k < E; k++) ks[(size_t)4 * b + k] = {r[k], 4 * b + k};
+    }
+    std::sort(ks.begin(), ks.end());
+    for (int p = 0; p < E; p++) check_lookup[p] = ks[(size_t)p].second / dv;
+    std::vector<int> conf;
+    for (int c = 0; c < m; c++)
+        for (int a = 1; a < dc; a++) {
+            bool rep = false;
+            for (int b = 0; b < a; b++) rep |= (check_lookup[(size_t)c * dc + b] == check_lookup[(size_t)c * dc + a]);
+            if (rep) conf.push_back(c * dc + a);
+        }
+    if (conf.size() > 512) return 0;
+    auto holds = [&](int c, int v, int skip) {
+        for (int j = 0; j < dc; j++) if (j != skip && check_lookup[(size_t)c * dc + j] == v) return true;
+        return false;
+    };
+    for (size_t i = 0; i < conf.size(); i++) {
+        const int c = conf[i] / dc, a = conf[i] % dc;
+        const int v = check_lookup[(size_t)c * dc + a];
+        bool rep = false;
+        for (int b = 0; b < a; b++) rep |= (check_lookup[(size_t)c * dc + b] == v);
+        if (!rep) continue;
+        for (uint32_t tries = 0; tries < 65536u; tries++) {
+            uint32_t r[4] = {((uint32_t)i << 16) | tries, g_lo, g_hi, 0x52455052u};
+            philox4x32_10(r, k0, k1);
+            const int s2 = (int)(((uint64_t)r[0] * (uint32_t)E) >> 32);
+            const int c2 = s2 / dc, j2 = s2 % dc;
+            if (c2 == c) continue;
+            const int v2 = check_lookup[s2];
+            if (holds(c, v2, a) || holds(c2, v, j2)) continue;
+            check_lookup[(size_t)c * dc + a] = v2;
+            check_lookup[s2] = v;
+            break;
+        }
+    }
+    return 1;
+}
 
 }  // namespace
 
@@ -144,4 +203,16 @@ extern "C" int ldpc_b200_generate_graph(int n, int dv, int dc, uint64_t seed, in
         return 1;
     }
     return 0;
+}
+
+// Graph `index` of the in-kernel ensemble generator for `graph_seed` (host twin of e1_graphgen.cuh), with the
+// (variable_lookup, check_lookup) contract of random_code_generator.c.  n*dv must be < 65536.
+extern "C" int ldpc_b200_generate_graph_indexed(int n, int dv, int dc, uint64_t graph_seed, uint64_t index,
+                                                int* variable_lookup, int* check_lookup) {
+    if (n <= 0 || dv <= 0 || dc <= 0 || !variable_lookup || !check_lookup) return 0;
+    const long long E = (long long)n * dv;
+    if (E % dc != 0 || E > 65535 || dc > n) return 0;
+    if (!generate_device_compatible(n, dv, dc, graph_seed, index, check_lookup)) return 0;
+    build_variable_lookup(check_lookup, n, (int)(E / dc), dv, dc, variable_lookup);
+    return 1;
 }

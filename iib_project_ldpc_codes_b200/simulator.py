@@ -198,12 +198,16 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
 
 
 def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=4096,
-                   wall_clock_limit=43000, gen_mode=1):
+                   wall_clock_limit=43000, gen_mode=2):
     """Ensemble Monte-Carlo (parallel_simulator_expurgated.py:169-285): a fresh random graph per frame group.
 
-    Graph G of the run is generate_graph(n, dv, dc, seed*1000003 + G, gen_mode) and decodes the global frames
-    [G*F, G*F + frames_per_graph), F = frames_per_graph rounded up to 128 (ldpc_b200_mc_run_ensemble); the
-    200-block-error rule (:200) is checked every `stop_rule_graphs` graphs."""
+    gen_mode 2 (default): graph G is built by the kernel itself in shared memory (host twin:
+    generate_graph_indexed(n, dv, dc, seed, G)); gen_mode 0/1: generate_graph(n, dv, dc, seed*1000003 + G, gen_mode) on
+    a pool of host threads.  Graph G decodes the global frames [G*F, G*F + frames_per_graph), F = frames_per_graph
+    rounded up to 128 (ldpc_b200_mc_run_ensemble); the 200-block-error rule (:200) is checked every
+    `stop_rule_graphs` graphs."""
+    if gen_mode == 2 and n * dv > 65535:
+        gen_mode = 1
     eps = parameter_set["BEC"]
     num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
     n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]

@@ -76,6 +76,12 @@ int ldpc_b200_device_count(void);
  * swaps (needed for (4,8) and large n where rejection takes > 10^4 shuffles).  Returns 1 on success. */
 int ldpc_b200_generate_graph(int n, int dv, int dc, uint64_t seed, int mode, int *variable_lookup, int *check_lookup);
 
+/* Graph `index` of the in-kernel ensemble generator (gen_mode 2 of ldpc_b200_mc_run_ensemble) for `graph_seed`:
+ * Philox keys -> sort -> listed repeats repaired, bit-identical to what the kernel builds in shared memory.
+ * n*dv must be < 65536. */
+int ldpc_b200_generate_graph_indexed(int n, int dv, int dc, uint64_t graph_seed, uint64_t index,
+                                     int *variable_lookup, int *check_lookup);
+
 /* Upload a Tanner graph: variable_to_check_list [n][dv], check_to_variable_list [n-k][dc], int32,
  * the layouts of message_passing.c:7.  k must equal n - n*dv/dc. */
 int ldpc_b200_graph_create(const int *variable_to_check_list, const int *check_to_variable_list,

@@ -117,3 +117,15 @@ def test_modified_density_evolution_matches_reference_values():
     from iib_project_ldpc_codes_b200.simulator import modified_density_evolution
     got = modified_density_evolution(0.40, 4, 3, 6)
     assert np.allclose(got, [0.4, 0.313756, 0.267938, 0.236467, 0.211673], atol=1e-6)
+
+
+@pytest.mark.parametrize("n,dv,dc", [(24, 3, 6), (1000, 3, 6), (2000, 4, 8), (60, 3, 4)])
+def test_indexed_generator_contract(built, n, dv, dc):
+    """Host twin of the in-kernel ensemble generator: simple regular graphs, reproducible, index-dependent."""
+    import iib_project_ldpc_codes_b200 as L
+    vl, cl = L.generate_graph_indexed(n, dv, dc, 12345, 7)
+    _check_contract(vl, cl, n, dv, dc)
+    vl2, cl2 = L.generate_graph_indexed(n, dv, dc, 12345, 7)
+    assert np.array_equal(cl, cl2)
+    _, cl3 = L.generate_graph_indexed(n, dv, dc, 12345, 8)
+    assert not np.array_equal(cl, cl3)

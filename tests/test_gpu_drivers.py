@@ -106,11 +106,31 @@ def test_mc_run_ensemble_matches_reference_per_graph(S, oracle, n, dv, dc, fpg, 
     assert np.array_equal(a + b, got)
 
 
+@pytest.mark.parametrize("n,dv,dc,fpg,graphs,exp", [(240, 3, 6, 128, 12, -1), (1000, 3, 6, 128, 6, 0), (2000, 4, 8, 128, 8, 0),
+                                                     (2000, 4, 8, 256, 3, -1), (96, 3, 6, 32, 50, 2), (60, 3, 4, 64, 20, -1),
+                                                     (600, 5, 10, 128, 5, -1)])
+def test_mc_run_ensemble_in_kernel_generator(S, oracle, n, dv, dc, fpg, graphs, exp):
+    """gen_mode 2: the kernel builds every graph itself in shared memory (Philox keys, bitonic sort, repair);
+    the host twin rebuilds the same graphs and the reference decodes the same frames on them."""
+    import iib_project_ldpc_codes_b200 as L
+    eps, seed, gseed, its, first = [0.35, 0.43], 99, 0xC0FFEE1234, 60, 7
+    got, st = L.mc_run_ensemble(n, dv, dc, eps, seed, graphs, its, frames_per_graph=fpg, graph_seed=gseed, gen_mode=2,
+                                first_graph=first, expurgation=exp, return_stats=True)
+    F = (fpg + 127) // 128 * 128
+    want = np.zeros_like(got)
+    for g in range(first, first + graphs):
+        vl, cl = L.generate_graph_indexed(n, dv, dc, gseed, g)
+        srt = np.sort(cl, axis=1)
+        assert (srt[:, 1:] != srt[:, :-1]).all() and (np.bincount(cl.ravel(), minlength=n) == dv).all()
+        want += oracle.best().mc_run(vl, cl, n, n - n * dv // dc, dv, dc, eps, seed, g * F, fpg, its, exp, nthreads=4)
+    assert np.array_equal(got, want)
+
+
 def test_run_simulation_ensemble_expurgated(S, oracle):
     import iib_project_ldpc_codes_b200 as L
     p = {"BEC": 0.40, "expurgation": 0, "num_tests": 1000, "iterations": 40, "n": 240, "dv": 3, "dc": 6,
          "optimal": False, "message_passing": True, "seed": 3}
-    r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4)
+    r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4, gen_mode=1)
     graphs = r["graphs"]
     assert r["num_tests"] == graphs * 128 and r["num_tests"] >= 1000      # whole graphs, rounded up
     want = _ensemble_reference(oracle, L, 240, 3, 6, [0.40], 3, 3, 0, graphs, 128, 40, 0)[0]
