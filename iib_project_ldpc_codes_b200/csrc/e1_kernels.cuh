@@ -47,6 +47,14 @@ template <> struct alignas(16) VecT<4> { uint32_t a[4]; };
 
 #define LDPC_FORW _Pragma("unroll") for (int w = 0; w < WORDS; w++)
 
+// one LOP3 with an explicit truth table (nvcc splits e.g. the 3-input majority into two)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
 // raw device counter block per erasure point, all uint64:
 //   [0 .. cap]            per-iteration erasure sums (bin 0 = initial count), counted frames only
 //   [cap+1 .. cap+5]      block errors, bit errors, frames, counted frames, executed iterations
@@ -166,10 +174,13 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
                 const VecT<WORDS> b = x[s_c2v[(j + 1) * m_pad + c]];
                 const VecT<WORDS> d = x[s_c2v[(j + 2) * m_pad + c]];
                 LDPC_FORW {
-                    const uint32_t some = a.a[w] | b.a[w] | d.a[w];
-                    const uint32_t maj = (a.a[w] & b.a[w]) | (a.a[w] & d.a[w]) | (b.a[w] & d.a[w]);
-                    tw.a[w] = tw.a[w] | maj | (one.a[w] & some);
-                    one.a[w] |= some;
+                    const uint32_t some = lop3<0xFE>(a.a[w], b.a[w], d.a[w]);   // a | b | c
+                    const uint32_t maj = lop3<0xE8>(a.a[w], b.a[w], d.a[w]);    // majority(a, b, c)
+                    if (j == 0) { tw.a[w] = maj; one.a[w] = some; }
+                    else {
+                        tw.a[w] = lop3<0xFE>(tw.a[w], maj, one.a[w] & some);
+                        one.a[w] |= some;
+                    }
                 }
             }
 #pragma unroll
@@ -216,7 +227,7 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
         LDPC_FORW nv.a[w] = 0u;
 #pragma unroll
         for (int j = 0; j < dv; j++) {
-            const int c = VG ? (int)__ldg(s_v2c + j * n_pad + i) : (int)s_v2c[j * n_pad + i];
+            const int c = VG ? (int)__ldg(s_v2c + (unsigned)(j * n_pad + i)) : (int)s_v2c[j * n_pad + i];
             const VecT<WORDS> tw = two[c];
             LDPC_FORW xn.a[w] &= tw.a[w];
             if (VALUES) {
