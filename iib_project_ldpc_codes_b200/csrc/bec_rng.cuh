@@ -65,4 +65,53 @@ __device__ __forceinline__ uint32_t bec_word(const BecParams& bp, uint32_t point
     return lt;
 }
 
+// ---- the same generator, split for the team-level draw of the E1 kernels (e1_kernels.cuh: team_draw) ----
+// One Philox block = four comparison levels.  bec_levels4 advances (lt, eq) by the four levels of block b.
+__device__ __forceinline__ void bec_block(const BecParams& bp, uint32_t point, uint64_t q, uint32_t var, int b,
+                                          uint32_t& lt, uint32_t& eq) {
+    uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
+    philox4x32_10(r0, r1, r2, r3, bp.seed_lo, bp.seed_hi);
+    const uint32_t r[4] = {r0, r1, r2, r3};
+    const uint32_t tb = bp.threshold << (4 * b);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const uint32_t m = (uint32_t)((int32_t)(tb << s) >> 31);
+        lt |= eq & ~r[s] & m;
+        eq &= ~(r[s] ^ m);
+    }
+}
+
+// true when block b was the last one bec_word would have executed for this word
+__device__ __forceinline__ bool bec_done_after(const BecParams& bp, int b, uint32_t eq) {
+    return eq == 0u || b == 7 || (bp.threshold << (4 * b + 4)) == 0u;
+}
+
+// level masks of the first two blocks (hoisted out of the per-variable loop by the caller)
+struct BecMasks8 { uint32_t m[8]; };
+__device__ __forceinline__ BecMasks8 bec_masks8(const BecParams& bp) {
+    BecMasks8 M;
+#pragma unroll
+    for (int s = 0; s < 8; s++) M.m[s] = (uint32_t)((int32_t)(bp.threshold << s) >> 31);
+    return M;
+}
+
+// blocks 0 and 1 without any exit test: identical (lt) to bec_word's first two blocks -- levels past the
+// point where bec_word would have stopped cannot change lt (eq == 0, or every remaining mask is zero).
+__device__ __forceinline__ void bec_first8(const BecParams& bp, const BecMasks8& M, uint32_t point, uint64_t q,
+                                           uint32_t var, uint32_t& lt, uint32_t& eq) {
+    lt = 0u; eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
+        philox4x32_10(r0, r1, r2, r3, bp.seed_lo, bp.seed_hi);
+        const uint32_t r[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t m = M.m[4 * b + s];
+            lt |= eq & ~r[s] & m;
+            eq &= ~(r[s] ^ m);
+        }
+    }
+}
+
 }  // namespace ldpc

@@ -94,6 +94,7 @@ struct E1Params {
     uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
     // Monte-Carlo work
     const BecParams* bec;  // [npoints]
+    uint32_t seed_lo, seed_hi;   // run seed (same in every bec[p]); a kernel parameter so the Philox round keys are uniform
     int npoints, cap, expurgation;
     unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
     unsigned long long num_frames;      // frames per point
@@ -259,6 +260,106 @@ __device__ __forceinline__ void red_add(unsigned long long* p, unsigned long lon
     if (v) atomicAdd(p, v);
 }
 
+// cold path of team_draw: finish a word in-thread when a continuation queue is full
+__device__ __noinline__ uint32_t bec_finish(const BecParams& bp, uint32_t point, unsigned long long q, uint32_t var,
+                                            int b, uint32_t eq) {
+    uint32_t lt = 0u;
+    for (;; b++) {
+        bec_block(bp, point, q, var, b, lt, eq);
+        if (bec_done_after(bp, b, eq)) break;
+    }
+    return lt;
+}
+
+// ---- channel draw for one frame group (channels.py:24-26), straight into shared memory ----
+// Same generator as bec_word (bec_rng.cuh), bit for bit, scheduled differently: bec_word runs Philox blocks
+// until the slowest of a word's 32 frames is decided, and inside a warp every thread waits for the slowest
+// word of 32 variables (3.2 blocks per word on average).  Here every word takes exactly two blocks (eight
+// levels, no exit tests); the ~12 % of words that still have an undecided frame are appended to a queue
+// (in the `two` array, idle during the draw) and continued one block per round by whichever thread picks
+// them up: 2.15 blocks per word.  Thread-local partial results: `red` (OR per word) and `cnt` (popcount).
+template <int WORDS, bool MASKED>
+__device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
+                                          unsigned long long q0, const uint32_t (&valid)[WORDS],
+                                          const uint32_t (&mask)[WORDS], VecT<WORDS>* x, uint32_t* qbuf,
+                                          uint32_t* qc, uint32_t (&red)[WORDS], uint32_t& cnt) {
+    LDPC_FORW red[w] = 0u;
+    cnt = 0u;
+    BecParams bp = bp_;
+    bp.seed_lo = P.seed_lo; bp.seed_hi = P.seed_hi;   // same values, but provably warp-uniform
+    if (bp.mode != 1) {   // eps == 0 or eps == 1
+        for (int i = t.tid; i < P.n; i += t.nthr) {
+            VecT<WORDS> xi;
+            LDPC_FORW {
+                xi.a[w] = bp.mode == 2 ? valid[w] : 0u;
+                red[w] |= xi.a[w];
+                cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
+            }
+            x[i] = xi;
+        }
+        return;
+    }
+    uint32_t* xs = reinterpret_cast<uint32_t*>(x);
+    uint2* q2 = reinterpret_cast<uint2*>(qbuf);
+    const uint32_t entries = (uint32_t)P.m * WORDS / 2u;
+    const uint32_t capB = entries / 8u, capA = entries - capB;
+    uint2* const qA = q2;
+    uint2* const qB = q2 + capA;
+    if (t.tid < 8) qc[t.tid] = 0u;
+    team_sync(t);
+    const BecMasks8 M = bec_masks8(bp);
+    const bool deeper = (bp.threshold << 8) != 0u;
+    for (int i = t.tid; i < P.n; i += t.nthr) {
+        VecT<WORDS> xi;
+        const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
+        LDPC_FORW {
+            uint32_t lt, eq;
+            bec_first8(bp, M, point, q0 + w, var, lt, eq);
+            eq &= valid[w];
+            if (eq != 0u && deeper) {
+                const uint32_t slot = atomicAdd(&qc[1], 1u);
+                if (slot < capA) qA[slot] = make_uint2((uint32_t)i * WORDS + w, eq);
+                else lt |= bec_finish(bp, point, q0 + w, var, 2, eq);
+            }
+            xi.a[w] = lt & valid[w];
+            red[w] |= xi.a[w];
+            cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
+        }
+        x[i] = xi;
+    }
+    team_sync(t);
+    for (int b = 2; b < 8; b++) {
+        const bool fromA = (b & 1) == 0;
+        const uint2* src = fromA ? qA : qB;
+        uint2* dst = fromA ? qB : qA;
+        const uint32_t capS = fromA ? capA : capB, capD = fromA ? capB : capA;
+        const uint32_t cin = min(qc[b - 1], capS);
+        if (cin == 0u) break;   // team-uniform
+        for (uint32_t e = t.tid; e < cin; e += t.nthr) {
+            const uint2 ent = src[e];
+            const uint32_t i = ent.x / WORDS, w = ent.x % WORDS;
+            const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : i;
+            uint32_t lt = 0u, eq = ent.y;
+            bec_block(bp, point, q0 + w, var, b, lt, eq);
+            if (!bec_done_after(bp, b, eq)) {
+                const uint32_t slot = atomicAdd(&qc[b], 1u);
+                if (slot < capD) dst[slot] = make_uint2(ent.x, eq);
+                else lt |= bec_finish(bp, point, q0 + w, var, b + 1, eq);
+            }
+            if (lt != 0u) {   // lt is a subset of the entry's eq, which was masked by `valid`
+                xs[ent.x] |= lt;
+#pragma unroll
+                for (int k = 0; k < WORDS; k++) {
+                    const uint32_t l = (w == (uint32_t)k) ? lt : 0u;
+                    red[k] |= l;
+                    cnt += __popc(MASKED ? (l & mask[k]) : l);
+                }
+            }
+        }
+        team_sync(t);
+    }
+}
+
 // Decode one frame group for the Monte-Carlo path.  MASKED pass: erasure sums restricted to `mask`.
 // Returns physical iterations executed; outputs the team-uniform masks / counts by reference.
 template <int WORDS, int DV, int DC, bool MASKED>
@@ -269,18 +370,8 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
                                         uint32_t& cnt, unsigned long long& exec_sum) {
     // draw the erasure pattern (channels.py:24-26) straight into shared memory
     uint32_t red[WORDS];
-    LDPC_FORW red[w] = 0u;
-    cnt = 0u;
-    for (int i = t.tid; i < P.n; i += t.nthr) {
-        VecT<WORDS> xi;
-        const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
-        LDPC_FORW {
-            xi.a[w] = bec_word(bp, point, q0 + w, var) & valid[w];
-            red[w] |= xi.a[w];
-            cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
-        }
-        x[i] = xi;
-    }
+    team_draw<WORDS, MASKED>(P, t, bp, point, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
+                             t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
     team_reduce<WORDS>(t, red, cnt);
     LDPC_FORW any[w] = red[w];
     if (t.tid == 0) hbuf[0] = cnt;

@@ -135,17 +135,8 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             const BecParams bp = P.bec[point];
             const unsigned long long q0 = P.first_word + gi * WORDS;
             uint32_t red[WORDS];
-            LDPC_FORW red[w] = 0u;
-            for (int i = t.tid; i < P.n; i += t.nthr) {
-                VecT<WORDS> xi;
-                const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
-                LDPC_FORW {
-                    xi.a[w] = bec_word(bp, point, q0 + w, var) & valid[w];
-                    red[w] |= xi.a[w];
-                    cnt += __popc(xi.a[w]);
-                }
-                x[i] = xi;
-            }
+            team_draw<WORDS, false>(P, t, bp, point, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
+                                    t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
             team_reduce<WORDS>(t, red, cnt);
             LDPC_FORW any[w] = red[w];
             if (t.tid == 0) hbuf[0] = cnt;

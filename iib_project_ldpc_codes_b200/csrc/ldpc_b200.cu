@@ -133,7 +133,7 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
         c.sm_v = off; if (values) off += align_up((uint32_t)g->n * 4 * words, 16);
         c.sm_p = off; if (values) off += align_up((uint32_t)g->m * 4 * words, 16);
         c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
-        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words) * 4, 16);
+        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words + 8) * 4, 16);
         return off;
     };
     int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
@@ -445,7 +445,7 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     fill_params(g, cfg, cap, P);
     P.c2v = g->placed[cfg.words].d_c2v; P.v2c = g->placed[cfg.words].d_v2c; P.var_orig = g->placed[cfg.words].d_var_orig;
     const unsigned long long W = 32ull * cfg.words;
-    P.bec = g->d_bec; P.npoints = npoints; P.expurgation = expurgation;
+    P.bec = g->d_bec; P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.npoints = npoints; P.expurgation = expurgation;
     P.first_word = first_frame / 32; P.num_frames = num_frames;
     P.groups_per_point = (num_frames + W - 1) / W;
     P.counters = g->d_raw; P.work_counter = g->d_work;
