@@ -67,15 +67,15 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
             }
             team_sync(t);
         }
-    // check_lookup in socket-major layout: position p -> check p/dc, socket p%dc, variable vals[p]/dv
-    for (int p = t.tid; p < E; p += t.nthr) s_c2v[(p % dc) * P.m_pad + p / dc] = (uint16_t)(vals[p] / dv);
+    // check_lookup in the packed socket-list layout (socklist.hpp): position p -> check p/dc, socket p%dc, variable vals[p]/dv
+    for (int p = t.tid; p < E; p += t.nthr) s_c2v[sock_off(dc, P.m_pad, p % dc, p / dc)] = (uint16_t)(vals[p] / dv);
     team_sync(t);
     // 3a. list the repeated positions
     for (int c = t.tid; c < P.m; c += t.nthr)
         for (int a = 1; a < dc; a++) {
-            const uint16_t v = s_c2v[a * P.m_pad + c];
+            const uint16_t v = s_c2v[sock_off(dc, P.m_pad, a, c)];
             bool rep = false;
-            for (int b = 0; b < a; b++) rep |= (s_c2v[b * P.m_pad + c] == v);
+            for (int b = 0; b < a; b++) rep |= (s_c2v[sock_off(dc, P.m_pad, b, c)] == v);
             if (rep) {
                 const uint32_t k = atomicAdd(&conf[0], 1u);
                 if (k < GG_MAX_CONFLICTS) conf[1 + k] = (uint32_t)(c * dc + a);
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
             while (k >= 0 && conf[1 + k] > v) { conf[2 + k] = conf[1 + k]; k--; }
             conf[2 + k] = v;
         }
-        auto at = [&](int c, int j) -> uint16_t& { return s_c2v[j * P.m_pad + c]; };
+        auto at = [&](int c, int j) -> uint16_t& { return s_c2v[sock_off(dc, P.m_pad, j, c)]; };
         auto holds = [&](int c, uint16_t v, int skip) {
             for (int j = 0; j < dc; j++) if (j != skip && at(c, j) == v) return true;
             return false;
@@ -121,9 +121,9 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
     team_sync(t);
     for (int p = t.tid; p < E; p += t.nthr) {
         const int c = p / dc, j = p % dc;
-        const int v = s_c2v[j * P.m_pad + c];
+        const int v = s_c2v[sock_off(dc, P.m_pad, j, c)];
         const uint32_t slot = atomicAdd(&fill[v], 1u);
-        if (slot < (uint32_t)dv) s_v2c[slot * P.n_pad + v] = (uint16_t)c;
+        if (slot < (uint32_t)dv) s_v2c[sock_off(dv, P.n_pad, (int)slot, v)] = (uint16_t)c;
     }
     team_sync(t);
     return true;

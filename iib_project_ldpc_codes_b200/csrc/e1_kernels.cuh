@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "bec_rng.cuh"
+#include "socklist.hpp"
 
 namespace ldpc {
 
@@ -94,6 +95,9 @@ struct E1Params {
     uint32_t sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;  // relative to the team base
     // Monte-Carlo work
     const BecParams* bec;  // [npoints]
+    // 2^16 and 2^16 * sizeof(VecT<WORDS>): multipliers of the index unpack (gather_offs); passed at run time so
+    // that ptxas keeps them as IMAD.WIDE on the idle FMA pipe instead of shift/mask chains on the ALU pipe
+    uint32_t k16, k16s, vec_bytes;
     uint32_t seed_lo, seed_hi;   // run seed (same in every bec[p]); a kernel parameter so the Philox round keys are uniform
     int npoints, cap, expurgation;
     unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
@@ -117,6 +121,7 @@ struct TeamCtx {
     int team_warps;
     int bar_id;
     uint32_t* scr;   // team scratch (shared)
+    uint32_t sa_x, sa_t;     // shared-window addresses of the team's x[] and two[]
 };
 
 __device__ __forceinline__ void team_sync(const TeamCtx& t) {
@@ -154,6 +159,74 @@ __device__ __forceinline__ void team_reduce(const TeamCtx& t, uint32_t (&ors)[NO
 #include "e1_graphgen.cuh"
 namespace ldpc {
 
+// ---- packed socket lists (socklist.hpp): all D neighbour slots of `node` with one or two vector loads ----
+template <bool GLOBAL> __device__ __forceinline__ uint2 sl_ld64(const uint16_t* p) {
+    return GLOBAL ? __ldg(reinterpret_cast<const uint2*>(p)) : *reinterpret_cast<const uint2*>(p);
+}
+template <bool GLOBAL> __device__ __forceinline__ uint32_t sl_ld32(const uint16_t* p) {
+    return GLOBAL ? __ldg(reinterpret_cast<const uint32_t*>(p)) : *reinterpret_cast<const uint32_t*>(p);
+}
+template <bool GLOBAL> __device__ __forceinline__ uint32_t sl_ld16(const uint16_t* p) {
+    return GLOBAL ? (uint32_t)__ldg(p) : (uint32_t)*p;
+}
+// Shared-window addresses of the D state vectors a node gathers: addr[j] = base + slot_j * sizeof(VecT).
+// A packed pair q = lo | hi << 16 is taken apart by multiply-adds on the FMA pipe (no shifts or masks on the
+// ALU pipe, which carries the decoder's LOP3 work); the multipliers are run-time values (E1Params) so that
+// ptxas does not turn them back into shift/mask chains:
+//     t = q * 2^16                        -> t.hi = hi,  t.lo = lo << 16           (IMAD.WIDE)
+//     addr_hi = t.hi * S + base                                                     (IMAD)
+//     addr_lo = hi32(t.lo * (2^16 * S) + (base << 32)) = lo * S + base              (IMAD.HI)
+// FMA_UNPACK = false: plain shift/mask unpack (ALU pipe) -- better for W <= 64, where the LOP3 work per node is
+// small and the extra IMAD.WIDE latency is not.
+template <int D, bool GLOBAL, bool FMA_UNPACK>
+__device__ __forceinline__ void gather_addrs(const E1Params& P, const uint16_t* __restrict__ list, int pad, int node,
+                                             uint32_t base, uint32_t vec_bytes, uint32_t (&addr)[D]) {
+    constexpr int NQ = D / 4, REM = D % 4;
+    const unsigned long long add = (unsigned long long)base << 32;
+    auto pair = [&](uint32_t q, uint32_t& a_lo, uint32_t& a_hi) {
+        if (FMA_UNPACK) {
+            const unsigned long long t = (unsigned long long)q * P.k16;
+            a_hi = (uint32_t)(t >> 32) * P.vec_bytes + base;
+            a_lo = (uint32_t)(((unsigned long long)(uint32_t)t * P.k16s + add) >> 32);
+        } else {
+            a_lo = (q & 0xFFFFu) * vec_bytes + base;
+            a_hi = (q >> 16) * vec_bytes + base;
+        }
+    };
+#pragma unroll
+    for (int g = 0; g < NQ; g++) {
+        const uint2 q = sl_ld64<GLOBAL>(list + ((size_t)g * pad + node) * 4);
+        pair(q.x, addr[4 * g], addr[4 * g + 1]);
+        pair(q.y, addr[4 * g + 2], addr[4 * g + 3]);
+    }
+    if (REM >= 2) {
+        const uint32_t pr = sl_ld32<GLOBAL>(list + (size_t)4 * NQ * pad + (size_t)node * 2);
+        pair(pr, addr[4 * NQ], addr[4 * NQ + 1]);
+    }
+    if (REM & 1) addr[D - 1] = sl_ld16<GLOBAL>(list + (size_t)(D - 1) * pad + node) * (FMA_UNPACK ? P.vec_bytes : vec_bytes) + base;
+}
+
+// state vector at a shared-window address (LDS / LDS.64 / LDS.128).  Deliberately neither volatile nor a
+// memory clobber (that would pin the loads behind the L2 index loads of the next unrolled variable): the
+// address always derives from index loads issued after the phase's team barrier, and within a phase the
+// array gathered from (x or two) is never the array stored to, so no reordering the compiler may do is visible.
+template <int WORDS> __device__ __forceinline__ VecT<WORDS> lds_vec(uint32_t a);
+template <> __device__ __forceinline__ VecT<1> lds_vec<1>(uint32_t a) {
+    VecT<1> v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v.a[0]) : "r"(a));
+    return v;
+}
+template <> __device__ __forceinline__ VecT<2> lds_vec<2>(uint32_t a) {
+    VecT<2> v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.a[0]), "=r"(v.a[1]) : "r"(a));
+    return v;
+}
+template <> __device__ __forceinline__ VecT<4> lds_vec<4>(uint32_t a) {
+    VecT<4> v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.a[0]), "=r"(v.a[1]), "=r"(v.a[2]), "=r"(v.a[3]) : "r"(a));
+    return v;
+}
+
 // ---- check phase:  two[c] = [>= 2 erased sockets]  (message_passing.c:24-45 collapsed) ----
 template <int WORDS, int DV, int DC, bool VALUES>
 __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t, const uint16_t* __restrict__ s_c2v,
@@ -169,11 +242,12 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
             // sockets in triples: "some" = a|b|c and "at least two" = majority(a,b,c) are one LOP3 each,
             // and triples combine with two |= maj | (one & some): 7 logic ops per word for dc = 6 instead
             // of 12, with a dependency depth of 3 instead of 6
+            uint32_t addr[DC ? DC : 1];
+            gather_addrs<DC ? DC : 1, false, WORDS == 4>(P, s_c2v, m_pad, c, t.sa_x, (uint32_t)sizeof(VecT<WORDS>), addr);
+            auto X = [&](int j) { return lds_vec<WORDS>(addr[j]); };
 #pragma unroll
             for (int j = 0; j + 2 < DC; j += 3) {
-                const VecT<WORDS> a = x[s_c2v[j * m_pad + c]];
-                const VecT<WORDS> b = x[s_c2v[(j + 1) * m_pad + c]];
-                const VecT<WORDS> d = x[s_c2v[(j + 2) * m_pad + c]];
+                const VecT<WORDS> a = X(j), b = X(j + 1), d = X(j + 2);
                 LDPC_FORW {
                     const uint32_t some = lop3<0xFE>(a.a[w], b.a[w], d.a[w]);   // a | b | c
                     const uint32_t maj = lop3<0xE8>(a.a[w], b.a[w], d.a[w]);    // majority(a, b, c)
@@ -186,13 +260,13 @@ __device__ __forceinline__ void check_phase(const E1Params& P, const TeamCtx& t,
             }
 #pragma unroll
             for (int j = DC - DC % 3; j < DC; j++) {   // dc not a multiple of 3: the last one or two sockets
-                const VecT<WORDS> xv = x[s_c2v[j * m_pad + c]];
+                const VecT<WORDS> xv = X(j);
                 LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < dc; j++) {
-                const int v = s_c2v[j * m_pad + c];
+                const int v = s_c2v[sock_off(dc, m_pad, j, c)];
                 const VecT<WORDS> xv = x[v];
                 LDPC_FORW { tw.a[w] |= one.a[w] & xv.a[w]; one.a[w] |= xv.a[w]; }
                 if (VALUES) {
@@ -226,10 +300,13 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
         const VecT<WORDS> xi = x[i];
         VecT<WORDS> xn = xi, nv;
         LDPC_FORW nv.a[w] = 0u;
+        uint32_t addr[DV ? DV : 1];
+        if (DV) gather_addrs<DV ? DV : 1, VG, WORDS == 4>(P, s_v2c, n_pad, i, t.sa_t, (uint32_t)sizeof(VecT<WORDS>), addr);
 #pragma unroll
         for (int j = 0; j < dv; j++) {
-            const int c = VG ? (int)__ldg(s_v2c + (unsigned)(j * n_pad + i)) : (int)s_v2c[j * n_pad + i];
-            const VecT<WORDS> tw = two[c];
+            const int c = DV ? (int)((addr[DV ? j : 0] - t.sa_t) / (uint32_t)sizeof(VecT<WORDS>))   // only used by VALUES
+                             : (int)sl_ld16<VG>(s_v2c + sock_off(dv, n_pad, j, i));
+            const VecT<WORDS> tw = DV ? lds_vec<WORDS>(addr[DV ? j : 0]) : two[c];
             LDPC_FORW xn.a[w] &= tw.a[w];
             if (VALUES) {
                 const VecT<WORDS> pr = par[c];
@@ -433,6 +510,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
     VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
     // scratch map: [0 .. 32*(2*WORDS+1))  reduce area ; then [work slot (2 words)] ; then rf[32*WORDS]
@@ -619,6 +697,7 @@ __global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_decode_kernel(const __gr
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<1>* x = reinterpret_cast<VecT<1>*>(base + P.sm_x);
     VecT<1>* two = reinterpret_cast<VecT<1>*>(base + P.sm_t);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
     VecT<1>* val = reinterpret_cast<VecT<1>*>(base + P.sm_v);
     VecT<1>* par = reinterpret_cast<VecT<1>*>(base + P.sm_p);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);

@@ -69,6 +69,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
     VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
     uint32_t* xs = reinterpret_cast<uint32_t*>(x);
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);

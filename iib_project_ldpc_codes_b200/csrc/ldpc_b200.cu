@@ -72,8 +72,8 @@ struct ldpc_b200_graph {
     int n = 0, k = 0, m = 0, dv = 0, dc = 0, device = 0;
     int n_pad = 0, m_pad = 0;
     std::vector<int> v2c, c2v;     // host copies, reference layouts
-    uint16_t* d_c2v16 = nullptr;   // socket-major [dc][m_pad]
-    uint16_t* d_v2c16 = nullptr;   // socket-major [dv][n_pad]
+    uint16_t* d_c2v16 = nullptr;   // packed socket lists (socklist.hpp), dc*m_pad uint16
+    uint16_t* d_v2c16 = nullptr;   // packed socket lists, dv*n_pad uint16
     int sm_count = 0, smem_optin = 0;
     // bank-conflict-aware placements for the Monte-Carlo kernel, one per words-per-group (index = words)
     struct Placed {
@@ -185,6 +185,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     memset(&P, 0, sizeof P);
     P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
     P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
+    P.k16 = 65536u; P.vec_bytes = 4u * (uint32_t)c.words; P.k16s = 65536u * P.vec_bytes;
     P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0;
     P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
@@ -229,8 +230,8 @@ extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int
     cudaDeviceGetAttribute(&g->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (n <= 65535) {
         std::vector<uint16_t> h_c((size_t)dc * g->m_pad, 0), h_v((size_t)dv * g->n_pad, 0);
-        for (int c = 0; c < m; c++) for (int j = 0; j < dc; j++) h_c[(size_t)j * g->m_pad + c] = (uint16_t)c2v[(size_t)c * dc + j];
-        for (int i = 0; i < n; i++) for (int j = 0; j < dv; j++) h_v[(size_t)j * g->n_pad + i] = (uint16_t)v2c[(size_t)i * dv + j];
+        for (int c = 0; c < m; c++) for (int j = 0; j < dc; j++) h_c[sock_off(dc, g->m_pad, j, c)] = (uint16_t)c2v[(size_t)c * dc + j];
+        for (int i = 0; i < n; i++) for (int j = 0; j < dv; j++) h_v[sock_off(dv, g->n_pad, j, i)] = (uint16_t)v2c[(size_t)i * dv + j];
         const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16);
         cudaError_t e = cudaMalloc(&g->d_c2v16, bc);
         if (e == cudaSuccess) e = cudaMalloc(&g->d_v2c16, bv);
@@ -360,8 +361,8 @@ static int ensure_placement(ldpc_b200_graph* g, int words) {
     Placement P;
     place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, P);
     std::vector<uint16_t> h_c((size_t)g->dc * g->m_pad, 0), h_v((size_t)g->dv * g->n_pad, 0), h_o((size_t)g->n_pad, 0);
-    for (int c = 0; c < g->m; c++) for (int j = 0; j < g->dc; j++) h_c[(size_t)j * g->m_pad + c] = (uint16_t)P.c2v[(size_t)c * g->dc + j];
-    for (int i = 0; i < g->n; i++) for (int j = 0; j < g->dv; j++) h_v[(size_t)j * g->n_pad + i] = (uint16_t)P.v2c[(size_t)i * g->dv + j];
+    for (int c = 0; c < g->m; c++) for (int j = 0; j < g->dc; j++) h_c[sock_off(g->dc, g->m_pad, j, c)] = (uint16_t)P.c2v[(size_t)c * g->dc + j];
+    for (int i = 0; i < g->n; i++) for (int j = 0; j < g->dv; j++) h_v[sock_off(g->dv, g->n_pad, j, i)] = (uint16_t)P.v2c[(size_t)i * g->dv + j];
     for (int i = 0; i < g->n; i++) h_o[i] = (uint16_t)P.var_orig[i];
     const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16), bo = align_up((uint32_t)(h_o.size() * 2), 16);
     CUDA_TRY(cudaMalloc(&pl.d_c2v, bc)); CUDA_TRY(cudaMalloc(&pl.d_v2c, bv)); CUDA_TRY(cudaMalloc(&pl.d_var_orig, bo));
