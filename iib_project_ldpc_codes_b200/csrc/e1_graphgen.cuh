@@ -6,7 +6,7 @@
 // check (:39-47).  Here every team of the E1 kernel builds the graph of its work item itself, in shared
 // memory, from a counter-based key, so ensemble mode needs neither host cores nor PCIe:
 //   1. keys:    key[s] = Philox4x32-10(counter (s>>2, G_lo, G_hi, 'GRAH'), key = graph seed)[s & 3]
-//   2. permute: bitonic sort of (key, s) in shared memory; position p of the sorted order carries socket s
+//   2. permute: sockets in ascending (key, s) order (bucket sort in shared memory); position p carries socket s
 //   3. repair:  every position (c, a) whose variable already occurs at an earlier socket of check c is
 //               listed (ascending); one thread walks the list and swaps the socket with a pseudo-random
 //               socket of another check when the swap leaves both checks repeat-free (same rule as
@@ -32,43 +32,97 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
                                                     unsigned char* team_base, unsigned long long G,
                                                     uint16_t* s_c2v, uint16_t* s_v2c) {
     const int dv = DV ? DV : P.dv, dc = DC ? DC : P.dc;
-    const int E = P.n * dv, epad = Gp.epad;
-    uint32_t* keys = reinterpret_cast<uint32_t*>(team_base + Gp.sm_keys);
-    uint16_t* vals = reinterpret_cast<uint16_t*>(team_base + Gp.sm_vals);
+    const int E = P.n * dv;
+    uint32_t* srt = reinterpret_cast<uint32_t*>(team_base + Gp.sm_sort);    // [E] (key high bits | socket id), sorted
+    uint32_t* bkt = reinterpret_cast<uint32_t*>(team_base + Gp.sm_bkt);     // [nb] bucket counts -> ends
+    uint32_t* part = bkt + (1u << Gp.nb_log2);                              // [nthr] scan partials
     uint32_t* fill = reinterpret_cast<uint32_t*>(team_base + Gp.sm_fill);
     uint32_t* conf = reinterpret_cast<uint32_t*>(team_base + Gp.sm_conf);   // [0] = count, [1..] = positions
     const uint32_t g_lo = (uint32_t)G, g_hi = (uint32_t)(G >> 32);
+    const int nb = 1 << Gp.nb_log2, bsh = 32 - Gp.nb_log2;
+    const uint32_t idmask = (1u << Gp.id_bits) - 1u;
+    auto full_key = [&](uint32_t sock) {
+        uint32_t r0 = sock >> 2, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_KEYS;
+        philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
+        const uint32_t k = sock & 3u;
+        return k == 0 ? r0 : k == 1 ? r1 : k == 2 ? r2 : r3;
+    };
 
-    // 1. keys
-    for (int b = t.tid; b < epad / 4; b += t.nthr) {
+    // 2. the permutation = sockets in ascending (key, socket) order.  Bucket sort instead of a full sorting
+    //    network: count the keys per bucket (top bits), prefix-sum, scatter (key high bits | socket) words,
+    //    then every bucket (a handful of entries) is insertion-sorted by one thread.  Words that tie on the
+    //    stored key bits are ordered by the full keys, so the order is exactly the (key, socket) order.
+    for (int b = t.tid; b < nb; b += t.nthr) bkt[b] = 0u;
+    if (t.tid == 0) conf[0] = 0u;
+    team_sync(t);
+    for (int b = t.tid; b < (E + 3) / 4; b += t.nthr) {
+        uint32_t r0 = (uint32_t)b, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_KEYS;
+        philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
+        const uint32_t r[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (4 * b + k < E) atomicAdd(&bkt[r[k] >> bsh], 1u);
+    }
+    team_sync(t);
+    {   // exclusive scan of the bucket counts, in place: chunk sums -> one warp scans them -> chunk prefixes
+        const int L = (nb + t.nthr - 1) / t.nthr, lo = t.tid * L, hi = min(nb, lo + L);
+        uint32_t sum = 0;
+        for (int b = lo; b < hi; b++) sum += bkt[b];
+        part[t.tid] = sum;
+        team_sync(t);
+        if (t.warp == 0) {
+            const int per = (t.nthr + 31) / 32, p0 = t.lane * per, p1 = min(t.nthr, p0 + per);
+            uint32_t mine = 0;
+            for (int q = p0; q < p1; q++) mine += part[q];
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (t.lane >= d) inc += o;
+            }
+            uint32_t run = inc - mine;
+            for (int q = p0; q < p1; q++) { const uint32_t v = part[q]; part[q] = run; run += v; }
+        }
+        team_sync(t);
+        uint32_t run = part[t.tid];
+        for (int b = lo; b < hi; b++) { const uint32_t v = bkt[b]; bkt[b] = run; run += v; }
+    }
+    team_sync(t);
+    for (int b = t.tid; b < (E + 3) / 4; b += t.nthr) {
         uint32_t r0 = (uint32_t)b, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_KEYS;
         philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
         const uint32_t r[4] = {r0, r1, r2, r3};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int s = 4 * b + k;
-            keys[s] = s < E ? r[k] : 0xFFFFFFFFu;
-            vals[s] = s < E ? (uint16_t)s : (uint16_t)0xFFFFu;
+            const int sck = 4 * b + k;
+            if (sck < E) srt[atomicAdd(&bkt[r[k] >> bsh], 1u)] = (r[k] & ~idmask) | (uint32_t)sck;
         }
     }
-    if (t.tid == 0) conf[0] = 0u;
-    team_sync(t);
-    // 2. bitonic sort by (key, val)
-    for (int k = 2; k <= epad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t.tid; i < epad / 2; i += t.nthr) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));   // element without bit j
-                const int hi = lo | j;
-                const bool up = (lo & k) == 0;
-                const uint32_t ka = keys[lo], kb = keys[hi];
-                const uint16_t va = vals[lo], vb = vals[hi];
-                const bool gt = ka > kb || (ka == kb && va > vb);
-                if (gt == up) { keys[lo] = kb; keys[hi] = ka; vals[lo] = vb; vals[hi] = va; }
+    team_sync(t);   // bkt[b] is now the END of bucket b
+    for (int b = t.tid; b < nb; b += t.nthr) {
+        const int lo = b ? (int)bkt[b - 1] : 0, hi = (int)bkt[b];
+        for (int i = lo + 1; i < hi; i++) {
+            const uint32_t w = srt[i];
+            int k = i - 1;
+            while (k >= lo) {
+                const uint32_t u = srt[k];
+                bool greater;   // u > w in (key, socket) order?
+                if (((u ^ w) & ~idmask) != 0u) greater = u > w;
+                else {
+                    const uint32_t ku = full_key(u & idmask), kw = full_key(w & idmask);
+                    greater = ku > kw || (ku == kw && u > w);
+                }
+                if (!greater) break;
+                srt[k + 1] = u;
+                k--;
             }
-            team_sync(t);
+            srt[k + 1] = w;
         }
-    // check_lookup in the packed socket-list layout (socklist.hpp): position p -> check p/dc, socket p%dc, variable vals[p]/dv
-    for (int p = t.tid; p < E; p += t.nthr) s_c2v[sock_off(dc, P.m_pad, p % dc, p / dc)] = (uint16_t)(vals[p] / dv);
+    }
+    team_sync(t);
+    // check_lookup in the packed socket-list layout (socklist.hpp): position p -> check p/dc, socket p%dc,
+    // variable (socket at position p)/dv
+    for (int p = t.tid; p < E; p += t.nthr) s_c2v[sock_off(dc, P.m_pad, p % dc, p / dc)] = (uint16_t)((srt[p] & idmask) / dv);
     team_sync(t);
     // 3a. list the repeated positions
     for (int c = t.tid; c < P.m; c += t.nthr)

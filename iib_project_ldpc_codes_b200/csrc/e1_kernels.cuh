@@ -28,6 +28,9 @@ constexpr int E1_MAX_THREADS = 512;
 #ifndef LDPC_W64_THREADS
 #define LDPC_W64_THREADS 768
 #endif
+#ifndef LDPC_W128_THREADS
+#define LDPC_W128_THREADS 768
+#endif
 #ifndef LDPC_CHECK_UNROLL
 #define LDPC_CHECK_UNROLL 1
 #endif
@@ -39,7 +42,7 @@ constexpr int E1_MAX_THREADS = 512;
 #endif
 constexpr int kCheckUnroll = LDPC_CHECK_UNROLL, kVarUnroll = LDPC_VAR_UNROLL, kVarUnrollVG = LDPC_VAR_UNROLL_VG;
 // one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
-__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? 768 : LDPC_W64_THREADS); }
+__host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? LDPC_W128_THREADS : LDPC_W64_THREADS); }
 
 template <int WORDS> struct VecT;
 template <> struct alignas(4)  VecT<1> { uint32_t a[1]; };
@@ -67,8 +70,8 @@ __host__ __device__ inline int raw_stride(int cap) { return 2 * cap + 10; }
 struct GraphGenParams {
     uint32_t seed_lo, seed_hi;      // graph seed
     unsigned long long first_graph; // global index of graph 0 of this launch
-    int epad;                       // n*dv rounded up to a power of two
-    uint32_t sm_keys, sm_vals, sm_fill, sm_conf;   // byte offsets relative to the team base (alias the state region)
+    int nb_log2, id_bits;           // bucket count of the socket sort (log2), bits that hold a socket id
+    uint32_t sm_sort, sm_bkt, sm_fill, sm_conf;   // byte offsets relative to the team base (alias the state region)
     unsigned long long* fail_flag;  // incremented if a graph could not be generated
 };
 
