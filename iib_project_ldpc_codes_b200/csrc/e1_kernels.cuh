@@ -101,6 +101,7 @@ struct E1Params {
     // 2^16 and 2^16 * sizeof(VecT<WORDS>): multipliers of the index unpack (gather_offs); passed at run time so
     // that ptxas keeps them as IMAD.WIDE on the idle FMA pipe instead of shift/mask chains on the ALU pipe
     uint32_t k16, k16s, vec_bytes;
+    uint32_t draw_qcap;   // test hook: cap on the continuation queue of team_draw (0 = as large as `two` allows)
     uint32_t seed_lo, seed_hi;   // run seed (same in every bec[p]); a kernel parameter so the Philox round keys are uniform
     int npoints, cap, expurgation;
     unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
@@ -381,7 +382,8 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
     }
     uint32_t* xs = reinterpret_cast<uint32_t*>(x);
     uint2* q2 = reinterpret_cast<uint2*>(qbuf);
-    const uint32_t entries = (uint32_t)P.m * WORDS / 2u;
+    uint32_t entries = (uint32_t)P.m * WORDS / 2u;
+    if (P.draw_qcap && P.draw_qcap < entries) entries = P.draw_qcap;   // overflowing words finish in-thread (bec_finish)
     const uint32_t capB = entries / 8u, capA = entries - capB;
     uint2* const qA = q2;
     uint2* const qB = q2 + capA;

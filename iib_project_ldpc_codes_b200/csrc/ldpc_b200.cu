@@ -185,7 +185,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     memset(&P, 0, sizeof P);
     P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
     P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
-    P.k16 = 65536u; P.vec_bytes = 4u * (uint32_t)c.words; P.k16s = 65536u * P.vec_bytes;
+    P.draw_qcap = (uint32_t)std::max(0, tuning_env("LDPC_B200_DRAW_QCAP")); P.k16 = 65536u; P.vec_bytes = 4u * (uint32_t)c.words; P.k16s = 65536u * P.vec_bytes;
     P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0;
     P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
@@ -375,10 +375,54 @@ static int ensure_placement(ldpc_b200_graph* g, int words) {
     return LDPC_B200_OK;
 }
 
+// Scratch device buffers of the handle-less entry points.  cudaMalloc / cudaFree cost milliseconds (and now and
+// then tens of milliseconds) per call, so released buffers go back to a small per-device pool instead.
+struct DevPool {
+    std::mutex mu;
+    struct Item { int dev; size_t bytes; void* p; };
+    std::vector<Item> free_list;
+    size_t pooled = 0;
+    static constexpr size_t kMaxPooled = (size_t)1 << 30;
+    cudaError_t get(size_t bytes, void** out, size_t* got) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_list.size(); i++)
+                if (free_list[i].dev == dev && free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes + 4096 &&
+                    (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+            if (best >= 0) {
+                *out = free_list[best].p; *got = free_list[best].bytes;
+                pooled -= free_list[best].bytes;
+                free_list.erase(free_list.begin() + best);
+                return cudaSuccess;
+            }
+        }
+        *got = bytes;
+        return cudaMalloc(out, bytes);
+    }
+    void put(void* p, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (pooled + bytes <= kMaxPooled && free_list.size() < 64) {
+                free_list.push_back({dev, bytes, p});
+                pooled += bytes;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+};
+static DevPool g_dev_pool;
+
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    size_t bytes = 0;
+    ~DevBuf() { if (p) g_dev_pool.put(p, bytes); }
+    cudaError_t alloc(size_t want) { return g_dev_pool.get(want ? want : 1, &p, &bytes); }
 };
 
 #include "e2_host.inc"

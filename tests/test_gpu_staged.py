@@ -76,3 +76,21 @@ def test_staged_other_degrees(L, oracle):
     got, st = _run(g, 3, eps, seed, frames, its)
     want = oracle.best().mc_run(vl, cl, 2000, 1000, 4, 8, eps, seed, 0, frames, its, -1, nthreads=16)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("qcap", [1, 9, 64])
+def test_draw_queue_overflow_finishes_in_thread(L, qcap):
+    """team_draw continues undecided words from a shared-memory queue; when the queue is full the word is finished
+    in-thread (bec_finish).  A tiny queue (test hook LDPC_B200_DRAW_QCAP) must not change a single counter, in the
+    unstaged, staged and masked (expurgation) paths."""
+    vl, cl = L.generate_graph(504, 3, 6, seed=3, mode=1)
+    eps, seed, its = [0.37, 0.44], 99, 60
+    for frames, exp in ((40000 + 5, -1), (3000, -1), (3000, 2)):
+        g = L.Graph(vl, cl)
+        want = g.mc_run(eps, seed, frames, its, expurgation=exp)
+        os.environ["LDPC_B200_DRAW_QCAP"] = str(qcap)
+        try:
+            got = L.Graph(vl, cl).mc_run(eps, seed, frames, its, expurgation=exp)
+        finally:
+            os.environ.pop("LDPC_B200_DRAW_QCAP", None)
+        assert np.array_equal(got, want), f"qcap={qcap} frames={frames} expurgation={exp}"
