@@ -276,6 +276,9 @@ def main():
     n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
     vl, cl = L.generate_graph(n, dv, dc, seed=GRAPH_SEED, mode=1)
     g = L.Graph(vl, cl, device=local)
+    # the handle is reused for every step: let the one-time bank-conflict placement search run longer (public knob)
+    place_effort = max(2, min(8, 8000 // n))
+    g.set_place_effort(place_effort)
     frames = wl["frames"]
     npoints = len(eps)
     d_cnt = torch.zeros((npoints, cap + 6), dtype=torch.int64, device=dev)
@@ -377,7 +380,7 @@ def main():
             "edge_updates_per_s": eu_per_s,
             "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_point_per_gpu": frames,
                        "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED, "l2": "256 MiB flush write between steps",
-                       "engine": stats},
+                       "place_effort": place_effort, "engine": stats},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks}
 
     if not args.no_cpu_baseline and world >= 1:
@@ -400,6 +403,7 @@ def main():
         w1 = WORKLOADS["c1"]
         v1, c1 = L.generate_graph(w1["n"], 3, 6, seed=GRAPH_SEED, mode=1)
         g1 = L.Graph(v1, c1, device=local)
+        g1.set_place_effort(8)
         f1 = 20_000_000
         d1 = torch.zeros((1, w1["cap"] + 6), dtype=torch.int64, device=dev)
         for _ in range(2):
