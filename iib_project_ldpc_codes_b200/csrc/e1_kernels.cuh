@@ -84,6 +84,9 @@ struct E1Params {
     // geometry
     int team_warps, teams;
     int v2c_global;   // 1: variable-side lookups stay in global memory (not staged into shared memory)
+    int v2c_res;      // v2c_global: lookups of variables [0, v2c_res) are nevertheless resident in shared memory (as much
+                      // as fits; a multiple of the team's threads), only the rest is streamed from L2 every iteration
+    uint32_t sm_vres; // byte offset of that resident part (packed lists with pad = v2c_res)
     // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
     // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
     // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c
@@ -126,6 +129,7 @@ struct TeamCtx {
     int bar_id;
     uint32_t* scr;   // team scratch (shared)
     uint32_t sa_x, sa_t;     // shared-window addresses of the team's x[] and two[]
+    unsigned char* sm;       // start of the CTA's dynamic shared memory
 };
 
 __device__ __forceinline__ void team_sync(const TeamCtx& t) {
@@ -294,13 +298,17 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
                                           VecT<WORDS>* __restrict__ x, const VecT<WORDS>* __restrict__ two,
                                           VecT<WORDS>* __restrict__ val, const VecT<WORDS>* __restrict__ par,
                                           const uint32_t (&mask)[WORDS], uint32_t (&any)[WORDS],
-                                          uint32_t (&chg)[WORDS], uint32_t& cnt) {
+                                          uint32_t (&chg)[WORDS], uint32_t& cnt,
+                                          int first = 0, int last = -1, int pad = -1, bool reset = true) {
+    // variables [first, last) with lookups in `s_v2c` (packed lists of `pad` nodes); reset = false accumulates
     const int dv = DV ? DV : P.dv;
-    const int n = P.n, n_pad = P.n_pad;
-    LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
-    cnt = 0u;
+    const int n = last < 0 ? P.n : last, n_pad = pad < 0 ? P.n_pad : pad;
+    if (reset) {
+        LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
+        cnt = 0u;
+    }
 #pragma unroll(VG ? kVarUnrollVG : kVarUnroll)
-    for (int i = t.tid; i < n; i += t.nthr) {
+    for (int i = first + t.tid; i < n; i += t.nthr) {
         const VecT<WORDS> xi = x[i];
         VecT<WORDS> xn = xi, nv;
         LDPC_FORW nv.a[w] = 0u;
@@ -334,6 +342,22 @@ __device__ __forceinline__ void var_phase(const E1Params& P, const TeamCtx& t, c
             chg[w] |= xi.a[w] ^ xn.a[w];
             cnt += __popc(MASKED ? (xn.a[w] & mask[w]) : xn.a[w]);
         }
+    }
+}
+
+// variable phase of the Monte-Carlo kernels: shared-memory lists, or (large graphs) a resident part + an L2-streamed rest
+template <int WORDS, int DV, int DC, bool MASKED>
+__device__ __forceinline__ void mc_var_phase(const E1Params& P, const TeamCtx& t, const uint16_t* s_v2c, const uint16_t* s_vres,
+                                             VecT<WORDS>* x, const VecT<WORDS>* two, const uint32_t (&mask)[WORDS],
+                                             uint32_t (&any)[WORDS], uint32_t (&chg)[WORDS], uint32_t& cnt) {
+    if (!P.v2c_global) {
+        var_phase<WORDS, DV, DC, false, MASKED, false>(P, t, s_v2c, x, two, nullptr, nullptr, mask, any, chg, cnt);
+    } else {
+        // the streamed part first: its L2 latency overlaps the resident part of the warps that have none
+        var_phase<WORDS, DV, DC, false, MASKED, true>(P, t, P.v2c, x, two, nullptr, nullptr, mask, any, chg, cnt, P.v2c_res, -1, -1, true);
+        if (P.v2c_res)
+            var_phase<WORDS, DV, DC, false, MASKED, false>(P, t, s_vres, x, two, nullptr, nullptr, mask, any, chg, cnt, 0, P.v2c_res,
+                                                           P.v2c_res, false);
     }
 }
 
@@ -442,6 +466,28 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
     }
 }
 
+// stage the resident part of the variable-side lists (v2c_global): every packed array keeps its nodes [0, v2c_res)
+__device__ __forceinline__ void stage_v2c_resident(const E1Params& P, unsigned char* smem) {
+    if (!P.v2c_global || !P.v2c_res) return;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(smem + P.sm_vres);
+    const int dv = P.dv, nq = dv >> 2, rem = dv & 3, R = P.v2c_res, n_pad = P.n_pad;
+    for (int a = 0; a < nq; a++) {   // 8 bytes per node
+        const uint2* g = reinterpret_cast<const uint2*>(P.v2c + (size_t)a * n_pad * 4);
+        uint2* d = reinterpret_cast<uint2*>(dst + (size_t)a * R * 4);
+        for (int i = threadIdx.x; i < R; i += blockDim.x) d[i] = __ldg(g + i);
+    }
+    if (rem >= 2) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(P.v2c + (size_t)4 * nq * n_pad);
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + (size_t)4 * nq * R);
+        for (int i = threadIdx.x; i < R; i += blockDim.x) d[i] = __ldg(g + i);
+    }
+    if (rem & 1) {
+        const uint16_t* g = P.v2c + (size_t)(dv - 1) * n_pad;
+        uint16_t* d = dst + (size_t)(dv - 1) * R;
+        for (int i = threadIdx.x; i < R; i += blockDim.x) d[i] = __ldg(g + i);
+    }
+}
+
 // Decode one frame group for the Monte-Carlo path.  MASKED pass: erasure sums restricted to `mask`.
 // Returns physical iterations executed; outputs the team-uniform masks / counts by reference.
 template <int WORDS, int DV, int DC, bool MASKED>
@@ -470,8 +516,7 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
         check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
         team_sync(t);
         uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-        if (P.v2c_global) var_phase<WORDS, DV, DC, false, MASKED, true>(P, t, P.v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
-        else var_phase<WORDS, DV, DC, false, MASKED, false>(P, t, s_v2c, x, two, nullptr, nullptr, mask, a2, c2, cnt);
+        mc_var_phase<WORDS, DV, DC, MASKED>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(t.sm + P.sm_vres), x, two, mask, a2, c2, cnt);
         LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
         team_reduce<2 * WORDS>(t, oc, cnt);
         if (t.tid == 0) hbuf[it + 1] = cnt;
@@ -501,6 +546,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
         for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
         if (!P.v2c_global) for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+        stage_v2c_resident(P, smem);
     }
     __syncthreads();
 
@@ -515,7 +561,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
     VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
-    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two); t.sm = smem;
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
     // scratch map: [0 .. 32*(2*WORDS+1))  reduce area ; then [work slot (2 words)] ; then rf[32*WORDS]
@@ -702,7 +748,7 @@ __global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_decode_kernel(const __gr
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<1>* x = reinterpret_cast<VecT<1>*>(base + P.sm_x);
     VecT<1>* two = reinterpret_cast<VecT<1>*>(base + P.sm_t);
-    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two); t.sm = smem;
     VecT<1>* val = reinterpret_cast<VecT<1>*>(base + P.sm_v);
     VecT<1>* par = reinterpret_cast<VecT<1>*>(base + P.sm_p);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);

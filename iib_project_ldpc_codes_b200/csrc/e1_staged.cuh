@@ -55,6 +55,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
         uint4* d1 = reinterpret_cast<uint4*>(s_v2c);
         for (int i = threadIdx.x; i < nc; i += blockDim.x) d0[i] = __ldg(g0 + i);
         if (!P.v2c_global) for (int i = threadIdx.x; i < nv; i += blockDim.x) d1[i] = __ldg(g1 + i);
+        stage_v2c_resident(P, smem);
     }
     __syncthreads();
 
@@ -69,7 +70,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
     unsigned char* base = smem + P.sm_team0 + (size_t)team * P.sm_team_stride;
     VecT<WORDS>* x = reinterpret_cast<VecT<WORDS>*>(base + P.sm_x);
     VecT<WORDS>* two = reinterpret_cast<VecT<WORDS>*>(base + P.sm_t);
-    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two);
+    t.sa_x = (uint32_t)__cvta_generic_to_shared(x); t.sa_t = (uint32_t)__cvta_generic_to_shared(two); t.sm = smem;
     uint32_t* xs = reinterpret_cast<uint32_t*>(x);
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
@@ -174,8 +175,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
             team_sync(t);
             uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-            if (P.v2c_global) var_phase<WORDS, DV, DC, false, false, true>(P, t, P.v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
-            else var_phase<WORDS, DV, DC, false, false, false>(P, t, s_v2c, x, two, nullptr, nullptr, valid, a2, c2, cnt);
+            mc_var_phase<WORDS, DV, DC, false>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(smem + P.sm_vres), x, two, valid, a2, c2, cnt);
             LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
             team_reduce<2 * WORDS>(t, oc, cnt);
             if (t.tid == 0) hbuf[age - lo + 1] = cnt;

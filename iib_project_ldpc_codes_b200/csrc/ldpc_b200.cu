@@ -60,6 +60,7 @@ struct E1Config {
     bool v2c_global = false;
     uint32_t smem = 0;
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
+    int v2c_res = 0; uint32_t sm_vres = 0;   // v2c_global: resident part of the variable-side lists
 };
 
 struct StagePlan {
@@ -176,6 +177,18 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
         c.sm_team0 = gbytes;
         c.sm_team_stride = tb;
         c.smem = gbytes + tb * teams;
+        c.v2c_res = 0; c.sm_vres = 0;
+        if (vg && tuning_env("LDPC_B200_V2C_RES") != 2) {
+            // whatever shared memory is left keeps the lists of the first variables resident (whole trips of the team)
+            const uint32_t off = align_up(c.smem, 16);
+            const uint32_t nthr = (uint32_t)tw * 32u;
+            if (limit > off) {
+                uint32_t res = (limit - off) / ((uint32_t)g->dv * 2u);
+                res = res / nthr * nthr;
+                if (res >= (uint32_t)g->n) res = (uint32_t)g->n / nthr * nthr;
+                if (res > 0) { c.v2c_res = (int)res; c.sm_vres = off; c.smem = off + res * (uint32_t)g->dv * 2u; }
+            }
+        }
         cfg = c;
         return true;
     }
@@ -187,7 +200,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
     P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
     P.draw_qcap = (uint32_t)std::max(0, tuning_env("LDPC_B200_DRAW_QCAP")); P.k16 = 65536u; P.vec_bytes = 4u * (uint32_t)c.words; P.k16s = 65536u * P.vec_bytes;
-    P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0;
+    P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0; P.v2c_res = c.v2c_res; P.sm_vres = c.sm_vres;
     P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
     P.cap = cap;
