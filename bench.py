@@ -277,7 +277,7 @@ def main():
     vl, cl = L.generate_graph(n, dv, dc, seed=GRAPH_SEED, mode=1)
     g = L.Graph(vl, cl, device=local)
     # the handle is reused for every step: let the one-time bank-conflict placement search run longer (public knob)
-    place_effort = max(2, min(8, 8000 // n))
+    place_effort = max(6, min(24, 24000 // n))
     g.set_place_effort(place_effort)
     frames = wl["frames"]
     npoints = len(eps)
@@ -403,7 +403,7 @@ def main():
         w1 = WORKLOADS["c1"]
         v1, c1 = L.generate_graph(w1["n"], 3, 6, seed=GRAPH_SEED, mode=1)
         g1 = L.Graph(v1, c1, device=local)
-        g1.set_place_effort(8)
+        g1.set_place_effort(24)
         f1 = 20_000_000
         d1 = torch.zeros((1, w1["cap"] + 6), dtype=torch.int64, device=dev)
         for _ in range(2):

@@ -368,8 +368,8 @@ static int ensure_events(ldpc_b200_graph* g) {
 
 // Build (once) the shared-memory placement of the graph for `words` words per node (relabel.hpp).
 // `frames` = frames the caller is about to decode (all points): only a very long run pays for a longer placement
-// search by itself (n = 1000: effort 8 takes 1.4 s on the host instead of 0.4 s and removes about a third of the
-// remaining conflict replays, ~3 % of the run time); callers that reuse a handle set it with ldpc_b200_set_place_effort.
+// search by itself (n = 1000: effort 24 takes 1.9 s on the host instead of 0.5 s and removes about a fifth of the
+// remaining conflict replays, ~1 % of the run time); callers that reuse a handle set it with ldpc_b200_set_place_effort.
 static int ensure_placement(ldpc_b200_graph* g, int words, double frames) {
     ldpc_b200_graph::Placed& pl = g->placed[words];
     int effort = g->place_effort;
@@ -377,8 +377,8 @@ static int ensure_placement(ldpc_b200_graph* g, int words, double frames) {
         const char* s = getenv("LDPC_B200_PLACE_EFFORT");
         if (s) effort = atoi(s);
         else {
-            effort = 2;
-            if (frames * (double)g->n >= 2e13) effort = std::max(2, std::min(8, 8000 / std::max(1, g->n)));
+            effort = 6;
+            if (frames * (double)g->n >= 2e13) effort = std::max(6, std::min(24, 24000 / std::max(1, g->n)));
         }
     }
     if (pl.ready && pl.effort >= effort) return LDPC_B200_OK;

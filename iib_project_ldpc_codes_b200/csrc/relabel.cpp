@@ -44,23 +44,6 @@ struct Search {
         if (delta > 0) { if (c >= S.d) cost++; c++; }
         else           { if (c > S.d) cost--; c--; }
     }
-    // remove (sign=-1) or add (sign=+1) node u of side S (other side O) at its current slot
-    void apply_node(SideState& S, SideState& O, int u, int sign) {
-        const int row = S.row_of(u), grp = S.grp_of(u);
-        for (int j = 0; j < S.d; j++) {
-            const int w = S.nbr[(size_t)u * S.d + j];
-            bump(S, row, O.grp_of(w), sign);          // u's row sees the neighbour's bank group
-            bump(O, O.row_of(w), grp, sign);          // the neighbour's row sees u's bank group
-        }
-    }
-    void swap_slots(SideState& S, SideState& O, int u1, int u2) {
-        apply_node(S, O, u1, -1);
-        apply_node(S, O, u2, -1);
-        std::swap(S.slot[u1], S.slot[u2]);
-        S.inv[S.slot[u1]] = u1; S.inv[S.slot[u2]] = u2;
-        apply_node(S, O, u1, +1);
-        apply_node(S, O, u2, +1);
-    }
     void init_counts() {
         std::fill(V.cnt.begin(), V.cnt.end(), 0);
         std::fill(C.cnt.begin(), C.cnt.end(), 0);
@@ -209,16 +192,50 @@ void place_graph(int n, int m, int dv, int dc, const int* v2c, const int* c2v, i
             // temperature than swaps of arbitrary pairs: n = 10^4, B = 16, same run time: 1.35x -> 1.21x of the
             // conflict-free wavefront count (n = 1000, B = 8: 1.14x -> 1.06x).
             const int u1 = (int)rng.below((uint32_t)A.N);
+            const bool group_swap = rng.below(2u) != 0;
             int s2;
-            if (rng.below(2u)) s2 = A.row_of(u1) * B + (int)rng.below((uint32_t)B);
+            if (group_swap) s2 = A.row_of(u1) * B + (int)rng.below((uint32_t)B);
             else s2 = (int)rng.below((uint32_t)A.rows) * B + A.grp_of(u1);
             if (s2 >= A.N) continue;
             const int u2 = A.inv[s2];
             if (u1 == u2) continue;
-            const long long before = S.cost;
-            S.swap_slots(A, O, u1, u2);
-            const long long delta = S.cost - before;
-            if (delta > 0 && rng.unit() >= exp(-(double)delta / T)) S.swap_slots(A, O, u1, u2);  // reject
+            // Net change per touched cell first (a cell can be hit several times), the cost change from that, and the
+            // tables are only written when the move is accepted -- most moves are rejected at low temperature.
+            SideState& Tb = group_swap ? O : A;   // the table the move changes
+            int* cells[4 * 64];
+            int dl[4 * 64];
+            int nc = 0;
+            auto add = [&](int row, int g, int k) {
+                int* c = &Tb.cnt[(size_t)row * B + g];
+                for (int q = 0; q < nc; q++) if (cells[q] == c) { dl[q] += k; return; }
+                cells[nc] = c; dl[nc] = k; nc++;
+            };
+            if (A.d > 64) continue;
+            if (group_swap) {
+                const int g1 = A.grp_of(u1), g2 = A.grp_of(u2);
+                for (int j = 0; j < A.d; j++) {
+                    const int r1 = O.row_of(A.nbr[(size_t)u1 * A.d + j]), r2 = O.row_of(A.nbr[(size_t)u2 * A.d + j]);
+                    add(r1, g1, -1); add(r1, g2, +1);
+                    add(r2, g2, -1); add(r2, g1, +1);
+                }
+            } else {
+                const int r1 = A.row_of(u1), r2 = A.row_of(u2);
+                for (int j = 0; j < A.d; j++) {
+                    const int ga = O.grp_of(A.nbr[(size_t)u1 * A.d + j]), gb = O.grp_of(A.nbr[(size_t)u2 * A.d + j]);
+                    add(r1, ga, -1); add(r2, ga, +1);
+                    add(r2, gb, -1); add(r1, gb, +1);
+                }
+            }
+            long long delta = 0;
+            for (int q = 0; q < nc; q++) {
+                const int c = *cells[q];
+                delta += std::max(0, c + dl[q] - Tb.d) - std::max(0, c - Tb.d);
+            }
+            if (delta > 0 && rng.unit() >= exp(-(double)delta / T)) continue;   // reject: nothing was touched
+            for (int q = 0; q < nc; q++) *cells[q] += dl[q];
+            S.cost += delta;
+            std::swap(A.slot[u1], A.slot[u2]);
+            A.inv[A.slot[u1]] = u1; A.inv[A.slot[u2]] = u2;
         }
     }
 
