@@ -5,6 +5,8 @@
 #include <string.h>
 #include <algorithm>
 #include <numeric>
+#include <stdlib.h>
+#include <thread>
 
 namespace ldpc {
 
@@ -137,6 +139,87 @@ void arrange_row(int cnt_nodes, int d, int B, const int* grp, int* order) {
     }
 }
 
+// Parallel version of the annealing loop in place_graph.  The run is cut into phases; a phase changes the slots of
+// ONE side only, and every thread owns a pseudo-random subset of that side's rows (a different partition each
+// phase, so nodes migrate between threads over time) and swaps only nodes inside rows it owns:
+//   * a row swap (same bank group, two owned rows) reads and writes cells of the own side's table in owned rows only;
+//   * a bank-group swap inside an owned row changes cells of the OTHER side's table, which other threads change
+//     too: relaxed atomic adds keep the counts exact, only the evaluation of a move can see a count that is being
+//     changed -- a little noise the annealing does not mind.
+// The other side's slots are constant during a phase.  The cost is recounted exactly afterwards by the caller.
+// Which thread wins a race is not reproducible, so neither is the placement; results never depend on it.
+void anneal_parallel(Search& S, int B, long long moves_per_thread, uint64_t seed, int T) {
+    const int phases = 96;
+    const double t0 = 0.25, t1 = 0.03;
+    const long long per_phase = std::max<long long>(1, moves_per_thread / phases);
+    for (int ph = 0; ph < phases; ph++) {
+        SideState& A = (ph & 1) ? S.C : S.V;
+        SideState& O = (ph & 1) ? S.V : S.C;
+        if (A.d > 64) continue;
+        const int full_rows = A.N / B;   // the partial last row stays where it is
+        if (full_rows < 2) continue;
+        std::vector<std::vector<int>> own(T);
+        {
+            Rng pr(seed * 7919u + (uint64_t)ph);
+            for (int r = 0; r < full_rows; r++) own[pr.below((uint32_t)T)].push_back(r);
+        }
+        const double Tlo = t0 * pow(t1 / t0, (double)ph / phases), Thi = t0 * pow(t1 / t0, (double)(ph + 1) / phases);
+        auto work = [&](int t) {
+            const std::vector<int>& rows = own[t];
+            if (rows.size() < 2) return;
+            Rng rng(seed + 0x9E37u * (uint64_t)(ph * 64 + t + 1));
+            for (long long it = 0; it < per_phase; it++) {
+                const double temp = Tlo + (Thi - Tlo) * (double)it / (double)per_phase;
+                const int r1 = rows[rng.below((uint32_t)rows.size())];
+                const int u1 = A.inv[r1 * B + (int)rng.below((uint32_t)B)];
+                const bool group_swap = rng.below(2u) != 0;
+                int s2;
+                if (group_swap) s2 = r1 * B + (int)rng.below((uint32_t)B);
+                else s2 = rows[rng.below((uint32_t)rows.size())] * B + A.grp_of(u1);
+                const int u2 = A.inv[s2];
+                if (u1 == u2) continue;
+                SideState& Tb = group_swap ? O : A;
+                int* cells[4 * 64];
+                int dl[4 * 64];
+                int nc = 0;
+                auto add = [&](int row, int g, int k) {
+                    int* c = &Tb.cnt[(size_t)row * B + g];
+                    for (int q = 0; q < nc; q++) if (cells[q] == c) { dl[q] += k; return; }
+                    cells[nc] = c; dl[nc] = k; nc++;
+                };
+                if (group_swap) {
+                    const int g1 = A.grp_of(u1), g2 = A.grp_of(u2);
+                    for (int j = 0; j < A.d; j++) {
+                        const int ra = O.row_of(A.nbr[(size_t)u1 * A.d + j]), rb = O.row_of(A.nbr[(size_t)u2 * A.d + j]);
+                        add(ra, g1, -1); add(ra, g2, +1);
+                        add(rb, g2, -1); add(rb, g1, +1);
+                    }
+                } else {
+                    const int ra = A.row_of(u1), rb = A.row_of(u2);
+                    for (int j = 0; j < A.d; j++) {
+                        const int ga = O.grp_of(A.nbr[(size_t)u1 * A.d + j]), gb = O.grp_of(A.nbr[(size_t)u2 * A.d + j]);
+                        add(ra, ga, -1); add(rb, ga, +1);
+                        add(rb, gb, -1); add(ra, gb, +1);
+                    }
+                }
+                long long delta = 0;
+                for (int q = 0; q < nc; q++) {
+                    const int c = __atomic_load_n(cells[q], __ATOMIC_RELAXED);
+                    delta += std::max(0, c + dl[q] - Tb.d) - std::max(0, c - Tb.d);
+                }
+                if (delta > 0 && rng.unit() >= exp(-(double)delta / temp)) continue;
+                for (int q = 0; q < nc; q++) if (dl[q]) __atomic_fetch_add(cells[q], dl[q], __ATOMIC_RELAXED);
+                std::swap(A.slot[u1], A.slot[u2]);
+                A.inv[A.slot[u1]] = u1; A.inv[A.slot[u2]] = u2;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+}
+
 double side_wavefronts(int N, int d, int B, const int* nbr_slots) {
     double total = 0;
     std::vector<int> load(B);
@@ -176,7 +259,19 @@ void place_graph(int n, int m, int dv, int dc, const int* v2c, const int* c2v, i
     S.C.cnt.assign((size_t)S.C.rows * B, 0);
     S.init_counts();
 
-    if (effort > 0 && n > 1 && m > 1) {
+    // threads: as many as give every thread >= 12 full rows of the smaller side, at most 16 (LDPC_B200_PLACE_THREADS overrides)
+    int threads = 1;
+    {
+        const char* e = getenv("LDPC_B200_PLACE_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        threads = e ? atoi(e) : std::min(std::min(hw > 0 ? hw : 1, 16), (m / B) / 12);
+        if (threads < 1) threads = 1;
+    }
+    if (effort > 0 && n > 1 && m > 1 && threads > 1) {
+        // `effort` is a time budget: every thread makes as many moves as the single-threaded search would
+        anneal_parallel(S, B, (long long)effort * 200 * ((long long)n + m), seed, threads);
+        S.init_counts();   // exact tables and cost again
+    } else if (effort > 0 && n > 1 && m > 1) {
         Rng rng(seed);
         const long long moves = (long long)effort * 200 * ((long long)n + m);
         const double t0 = 0.25, t1 = 0.03;
