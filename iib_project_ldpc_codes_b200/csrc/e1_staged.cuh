@@ -243,6 +243,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
                 uint32_t before = 0;
                 LDPC_FORW {
+                    if (D[w] == 0u) continue;   // team-uniform: no survivor in this word, nothing to transpose
                     const int s0 = 32 * j0 + t.lane;
                     uint4 r;
                     r.x = transpose32(s0 < P.n ? xs[s0 * WORDS + w] : 0u, t.lane);

@@ -536,6 +536,8 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
         rc = get_stage_plan(g, cfg, P, eps, npoints, seed, cap, st, &plan);
         if (rc) return rc;
         if (plan->nstages <= 1) plan = nullptr;
+        // the pilot (first call per plan key) pulls its groups from the same work counter: start from zero again
+        CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
     }
     const int slot = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
     if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));

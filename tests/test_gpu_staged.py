@@ -94,3 +94,20 @@ def test_draw_queue_overflow_finishes_in_thread(L, qcap):
         finally:
             os.environ.pop("LDPC_B200_DRAW_QCAP", None)
         assert np.array_equal(got, want), f"qcap={qcap} frames={frames} expurgation={exp}"
+
+
+def test_pilot_that_chooses_one_stage_leaves_no_trace(L, oracle):
+    """First call on a handle runs the stage pilot; when the plan comes out as ONE stage the unstaged kernel runs
+    right after it and must start from a clean work counter (regression: it skipped the groups the pilot had pulled)."""
+    vl, cl = L.generate_graph(504, 3, 6, seed=2, mode=1)
+    eps, seed, frames, its = [0.35, 0.42, 0.5], 11, 33000, 8
+    want = oracle.best().mc_run(vl, cl, 504, 252, 3, 6, eps, seed, 0, frames, its, -1, nthreads=16)
+    os.environ["LDPC_B200_REPACK_PCT"] = "100000"      # re-packing prohibitively expensive -> the plan has one stage
+    try:
+        g = L.Graph(vl, cl)
+        got, st = g.mc_run(eps, seed, frames, its, return_stats=True)
+        again = g.mc_run(eps, seed, frames, its)
+    finally:
+        os.environ.pop("LDPC_B200_REPACK_PCT", None)
+    assert st["stages"] == 1
+    assert np.array_equal(got, want) and np.array_equal(again, want)
