@@ -145,18 +145,22 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
         } else {
             const uint32_t* recs = S.spill_in + ((size_t)point * S.point_stride + gi * W) * S.rec_words;
             for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
+                VecT<WORDS> o[4];   // state vectors of variables s0, s0+32, s0+64, s0+96: whole-vector stores (no bank conflicts)
                 LDPC_FORW {
                     uint4 r = make_uint4(0, 0, 0, 0);
                     if ((valid[w] >> t.lane) & 1u)
                         r = *reinterpret_cast<const uint4*>(recs + (size_t)(w * 32 + t.lane) * S.rec_words + j0);
-                    const uint32_t c0 = transpose32(r.x, t.lane), c1 = transpose32(r.y, t.lane);
-                    const uint32_t c2 = transpose32(r.z, t.lane), c3 = transpose32(r.w, t.lane);
-                    const int s0 = 32 * j0 + t.lane;
-                    if (s0 < P.n) xs[s0 * WORDS + w] = c0;
-                    if (s0 + 32 < P.n) xs[(s0 + 32) * WORDS + w] = c1;
-                    if (s0 + 64 < P.n) xs[(s0 + 64) * WORDS + w] = c2;
-                    if (s0 + 96 < P.n) xs[(s0 + 96) * WORDS + w] = c3;
+                    if (valid[w] != 0u) {   // team-uniform
+                        o[0].a[w] = transpose32(r.x, t.lane); o[1].a[w] = transpose32(r.y, t.lane);
+                        o[2].a[w] = transpose32(r.z, t.lane); o[3].a[w] = transpose32(r.w, t.lane);
+                    } else {
+                        o[0].a[w] = 0u; o[1].a[w] = 0u; o[2].a[w] = 0u; o[3].a[w] = 0u;
+                    }
                 }
+                const int s0 = 32 * j0 + t.lane;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s0 + 32 * k < P.n) x[s0 + 32 * k] = o[k];
             }
             LDPC_FORW any[w] = valid[w];
             team_sync(t);
@@ -242,14 +246,20 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             uint32_t* out = S.spill_out + (size_t)point * S.point_stride * S.rec_words;
             for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
                 uint32_t before = 0;
+                const int s0 = 32 * j0 + t.lane;
+                VecT<WORDS> v[4];   // whole-vector loads of variables s0, s0+32, s0+64, s0+96 (no bank conflicts)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (s0 + 32 * k < P.n) v[k] = x[s0 + 32 * k];
+                    else { LDPC_FORW v[k].a[w] = 0u; }
+                }
                 LDPC_FORW {
                     if (D[w] == 0u) continue;   // team-uniform: no survivor in this word, nothing to transpose
-                    const int s0 = 32 * j0 + t.lane;
                     uint4 r;
-                    r.x = transpose32(s0 < P.n ? xs[s0 * WORDS + w] : 0u, t.lane);
-                    r.y = transpose32(s0 + 32 < P.n ? xs[(s0 + 32) * WORDS + w] : 0u, t.lane);
-                    r.z = transpose32(s0 + 64 < P.n ? xs[(s0 + 64) * WORDS + w] : 0u, t.lane);
-                    r.w = transpose32(s0 + 96 < P.n ? xs[(s0 + 96) * WORDS + w] : 0u, t.lane);
+                    r.x = transpose32(v[0].a[w], t.lane);
+                    r.y = transpose32(v[1].a[w], t.lane);
+                    r.z = transpose32(v[2].a[w], t.lane);
+                    r.w = transpose32(v[3].a[w], t.lane);
                     if ((D[w] >> t.lane) & 1u) {
                         const unsigned long long rec = sbase + before + __popc(D[w] & ((1u << t.lane) - 1u));
                         *reinterpret_cast<uint4*>(out + (size_t)rec * S.rec_words + j0) = r;
