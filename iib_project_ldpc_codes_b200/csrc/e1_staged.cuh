@@ -18,12 +18,20 @@
 namespace ldpc {
 
 // lane l holds row l; afterwards lane b holds column b  (out_b bit l = in_l bit b).  Warp-collective.
+// Five butterfly stages; stage j exchanges the off-diagonal j x j blocks with lane ^ j.  Every lane sends its word
+// rotated so that the bits its partner needs already sit in the partner's target positions (left by j from lanes
+// with bit j set, right by j from the others), and the receiver merges with one bit-select: 3 instructions per
+// stage (funnel shift, shuffle, LOP3) instead of shift/mask/select chains -- the re-packing between stages is
+// transposes more than anything else.
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
     for (int j = 16; j >= 1; j >>= 1) {
         const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t p = __shfl_xor_sync(0xFFFFFFFFu, x, j);
-        x = (lane & j) ? (((p >> j) & m) | (x & ~m)) : ((x & m) | ((p & m) << j));
+        const bool hi = (lane & j) != 0;
+        const uint32_t keep = hi ? (m << j) : m;                       // the bits this lane keeps
+        const uint32_t send = __funnelshift_l(x, x, hi ? j : 32 - j);  // rotate: left by j (hi) / right by j (lo)
+        const uint32_t p = __shfl_xor_sync(0xFFFFFFFFu, send, j);
+        x = (x & keep) | (p & ~keep);
     }
     return x;
 }
