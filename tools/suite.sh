@@ -1,4 +1,4 @@
-# measurement suite: tests, bench lines, launch list, ncu captures.  usage: bash tools/_suite.sh TAG
+# measurement suite: tests, bench lines, launch list, ncu captures.  usage: bash tools/suite.sh TAG
 TAG=${1:-r1x}
 O=gpurun_out
 set -x
