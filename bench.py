@@ -344,7 +344,7 @@ def main():
     roofline = {"bound": "smem" if e1 else "hbm", "achieved": achieved, "peak": smem_peak if e1 else hbm_peak,
                 "unit": "GB/s", "frac": achieved / (smem_peak if e1 else hbm_peak), "traffic": None,
                 "note": ("E1 keeps graph+state in shared memory: HBM sees only the counter REDs and the spill records of the "
-                         "staged pipeline (ncu, profiles/r1j_e1_staged_c2_w64_stage0_ncu_full.txt: 2.6 MB read + 0.63 GB written "
+                         "staged pipeline (ncu, profiles/r1j_e1_staged_c2_w64_stage0_ncu_full.txt: 1.7 MB read + 0.51 GB written "
                          "by the stage-0 launch of 1.2*10^6 frames, 5*10^-4 of its algorithmic shared-memory bytes); peak = "
                          "shared-memory read bandwidth measured on this GPU by ldpc_b200_smem_probe (conflict-free LDS.128 "
                          "from all SMs)")
