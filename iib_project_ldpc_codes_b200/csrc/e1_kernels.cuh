@@ -9,7 +9,7 @@
 //     (SURVEY.md 7.1), so one flooding iteration is, per check, dc gathered words combined with
 //         two |= one & w ; one |= w
 //     and, per variable, dv gathered `two` words ANDed into x.  No tensor-core shaped work.
-//   * The graph (socket-major uint16 index arrays) is staged ONCE per CTA in shared memory;
+//   * The graph (packed uint16 socket lists, socklist.hpp) is staged ONCE per CTA in shared memory;
 //     each team of warps owns a frame group whose state (x[n], two[m]) also lives in shared
 //     memory, so HBM is touched only by the final counter REDs (Monte-Carlo) or the
 //     pattern/result planes (batched decode).
@@ -76,7 +76,7 @@ struct GraphGenParams {
 };
 
 struct E1Params {
-    // graph (global memory, socket-major uint16: idx[j * pad + node])
+    // graph (global memory, packed uint16 socket lists: socklist.hpp)
     const uint16_t* c2v;
     const uint16_t* v2c;
     const uint16_t* var_orig;  // slot -> original variable id (keys the erasure generator); NULL = identity
