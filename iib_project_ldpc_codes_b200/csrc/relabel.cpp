@@ -214,8 +214,12 @@ void anneal_parallel(Search& S, int B, long long moves_per_thread, uint64_t seed
             }
         };
         std::vector<std::thread> th;
-        for (int t = 1; t < T; t++) th.emplace_back(work, t);
-        work(0);
+        std::vector<int> inline_work{0};
+        for (int t = 1; t < T; t++) {
+            try { th.emplace_back(work, t); }
+            catch (...) { inline_work.push_back(t); }   // no more threads to be had: this share runs on the caller's thread
+        }
+        for (int t : inline_work) work(t);
         for (auto& x : th) x.join();
     }
 }
