@@ -67,6 +67,7 @@ struct StagePlan {
     int nstages = 1;
     std::vector<int> cuts;   // [npoints][nstages+1]
     double predicted_inflation = 0;
+    unsigned long long pilot_frames = 0;   // frames per point the pilot decoded (a much larger run draws a better one)
 };
 
 struct ldpc_b200_graph {
@@ -532,8 +533,8 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     // staged path: survivors are re-packed between stages (e1_staged.cuh); exact, used when every frame
     // counts (no expurgation mask) and the run is long enough to amortise the pilot
     StagePlan* plan = nullptr;
-    if (expurgation < 0 && num_frames >= 32768 && tuning_env("LDPC_B200_STAGES") != 1) {
-        rc = get_stage_plan(g, cfg, P, eps, npoints, seed, cap, st, &plan);
+    if (expurgation < 0 && num_frames >= 8192 && tuning_env("LDPC_B200_STAGES") != 1) {
+        rc = get_stage_plan(g, cfg, P, eps, npoints, seed, cap, num_frames, st, &plan);
         if (rc) return rc;
         if (plan->nstages <= 1) plan = nullptr;
         // the pilot (first call per plan key) pulls its groups from the same work counter: start from zero again
