@@ -111,3 +111,21 @@ def test_pilot_that_chooses_one_stage_leaves_no_trace(L, oracle):
         os.environ.pop("LDPC_B200_REPACK_PCT", None)
     assert st["stages"] == 1
     assert np.array_equal(got, want) and np.array_equal(again, want)
+
+
+@pytest.mark.parametrize("frames", [8192, 9001, 20000])
+def test_small_runs_use_a_small_pilot_and_stay_exact(L, oracle, frames):
+    """From 8192 frames per point the staged pipeline is on, with a pilot of an eighth of the run (1024..8192 frames):
+    rough cut points from a tiny lifetime histogram must not change a single counter; a later, much larger run on the
+    same handle re-draws the pilot."""
+    vl, cl = L.generate_graph(1000, 3, 6, seed=4, mode=1)
+    eps, seed, its = [0.38, 0.41, 0.44], 21, 200
+    g = L.Graph(vl, cl)
+    got, st = g.mc_run(eps, seed, frames, its, return_stats=True)
+    want = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed, 0, frames, its, -1, nthreads=16)
+    assert st["stages"] > 1
+    assert np.array_equal(got, want)
+    big = 70000
+    got2 = g.mc_run(eps, seed + 1, big, its)
+    want2 = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed + 1, 0, big, its, -1, nthreads=16)
+    assert np.array_equal(got2, want2)
