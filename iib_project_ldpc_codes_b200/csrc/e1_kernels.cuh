@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include "bec_rng.cuh"
 #include "socklist.hpp"
+#include "e1_tmem.cuh"
 
 namespace ldpc {
 
@@ -87,6 +88,9 @@ struct E1Params {
     int v2c_res;      // v2c_global: lookups of variables [0, v2c_res) are nevertheless resident in shared memory (as much
                       // as fits; a multiple of the team's threads), only the rest is streamed from L2 every iteration
     uint32_t sm_vres; // byte offset of that resident part (packed lists with pad = v2c_res)
+    // socket lists in tensor memory (e1_tmem.cuh): ready-made gather addresses per thread, no lists in shared memory
+    int tm;                                 // 1: on (kernels instantiated with TM = true)
+    int tm_cpw, tm_trips_c, tm_trips_v;     // columns per warp, check / variable trips per thread
     // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
     // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
     // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c
@@ -130,6 +134,7 @@ struct TeamCtx {
     uint32_t* scr;   // team scratch (shared)
     uint32_t sa_x, sa_t;     // shared-window addresses of the team's x[] and two[]
     unsigned char* sm;       // start of the CTA's dynamic shared memory
+    uint32_t ta_c, ta_v;     // TM: tensor-memory addresses of this thread's check / variable columns
 };
 
 __device__ __forceinline__ void team_sync(const TeamCtx& t) {
@@ -232,6 +237,24 @@ template <> __device__ __forceinline__ VecT<2> lds_vec<2>(uint32_t a) {
 template <> __device__ __forceinline__ VecT<4> lds_vec<4>(uint32_t a) {
     VecT<4> v;
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.a[0]), "=r"(v.a[1]), "=r"(v.a[2]), "=r"(v.a[3]) : "r"(a));
+    return v;
+}
+
+// the same loads as volatile asm: for addresses that do NOT derive from a load issued after the phase barrier
+template <int WORDS> __device__ __forceinline__ VecT<WORDS> lds_vec_ordered(uint32_t a);
+template <> __device__ __forceinline__ VecT<1> lds_vec_ordered<1>(uint32_t a) {
+    VecT<1> v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.a[0]) : "r"(a) : "memory");
+    return v;
+}
+template <> __device__ __forceinline__ VecT<2> lds_vec_ordered<2>(uint32_t a) {
+    VecT<2> v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.a[0]), "=r"(v.a[1]) : "r"(a) : "memory");
+    return v;
+}
+template <> __device__ __forceinline__ VecT<4> lds_vec_ordered<4>(uint32_t a) {
+    VecT<4> v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.a[0]), "=r"(v.a[1]), "=r"(v.a[2]), "=r"(v.a[3]) : "r"(a) : "memory");
     return v;
 }
 
@@ -359,6 +382,138 @@ __device__ __forceinline__ void mc_var_phase(const E1Params& P, const TeamCtx& t
             var_phase<WORDS, DV, DC, false, MASKED, false>(P, t, s_vres, x, two, nullptr, nullptr, mask, any, chg, cnt, 0, P.v2c_res,
                                                            P.v2c_res, false);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same two phases with the socket lists in tensor memory (e1_tmem.cuh): the gather addresses of a node come
+// ready-made from tcgen05.ld, the addresses of the NEXT trip are requested as soon as this trip's gathers are
+// issued, and nothing but state vectors travels through the shared-memory pipe.
+// ------------------------------------------------------------------------------------------------
+template <int WORDS> __device__ __forceinline__ void sts_vec(uint32_t a, const VecT<WORDS>& v);
+template <> __device__ __forceinline__ void sts_vec<1>(uint32_t a, const VecT<1>& v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v.a[0]) : "memory");
+}
+template <> __device__ __forceinline__ void sts_vec<2>(uint32_t a, const VecT<2>& v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.a[0]), "r"(v.a[1]) : "memory");
+}
+template <> __device__ __forceinline__ void sts_vec<4>(uint32_t a, const VecT<4>& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.a[0]), "r"(v.a[1]), "r"(v.a[2]), "r"(v.a[3]) : "memory");
+}
+
+// two = [>= 2 of the DC gathered words have the bit set]; sockets in triples (see check_phase)
+template <int WORDS, int DC>
+__device__ __forceinline__ VecT<WORDS> check_two(const VecT<WORDS> (&v)[DC]) {
+    VecT<WORDS> one, tw;
+    LDPC_FORW { one.a[w] = 0u; tw.a[w] = 0u; }
+#pragma unroll
+    for (int j = 0; j + 2 < DC; j += 3) {
+        LDPC_FORW {
+            const uint32_t some = lop3<0xFE>(v[j].a[w], v[j + 1].a[w], v[j + 2].a[w]);
+            const uint32_t maj = lop3<0xE8>(v[j].a[w], v[j + 1].a[w], v[j + 2].a[w]);
+            if (j == 0) { tw.a[w] = maj; one.a[w] = some; }
+            else {
+                tw.a[w] = lop3<0xFE>(tw.a[w], maj, one.a[w] & some);
+                one.a[w] |= some;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = DC - DC % 3; j < DC; j++) LDPC_FORW { tw.a[w] |= one.a[w] & v[j].a[w]; one.a[w] |= v[j].a[w]; }
+    return tw;
+}
+
+// One trip = one node per thread.  Order inside a trip: wait for this trip's addresses, issue its gathers, request the
+// next trip's addresses into the same registers (the gathers have read them), then combine and store.
+template <int WORDS, int DC>
+__device__ __forceinline__ void check_phase_tm(const E1Params& P, const TeamCtx& t) {
+    const int trips = P.tm_trips_c;
+    const int full = P.m / t.nthr;          // trips in which every thread of the team has a check
+    const uint32_t step = (uint32_t)t.nthr * (uint32_t)sizeof(VecT<WORDS>);
+    uint32_t dst = t.sa_t + (uint32_t)t.tid * (uint32_t)sizeof(VecT<WORDS>);
+    uint32_t ta = t.ta_c;
+    uint32_t a[DC];
+    tm_ld<DC>(ta, a);
+    auto trip = [&](bool more, bool valid) {
+        tm_wait_ld<DC>(a);
+        VecT<WORDS> v[DC];
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < DC; j++) v[j] = lds_vec<WORDS>(a[j]);
+        }
+        ta += DC;
+        if (more) tm_ld<DC>(ta, a);   // warp-uniform
+        if (valid) sts_vec<WORDS>(dst, check_two<WORDS, DC>(v));
+        dst += step;
+    };
+#pragma unroll 2
+    for (int tr = 0; tr < full; tr++) trip(tr + 1 < trips, true);
+    if (full < trips) trip(false, full * t.nthr + t.tid < P.m);   // last trip: some lanes have no check
+}
+
+template <int WORDS, int DV, bool MASKED>
+__device__ __forceinline__ void var_phase_tm(const E1Params& P, const TeamCtx& t, const uint32_t (&mask)[WORDS],
+                                             uint32_t (&any)[WORDS], uint32_t (&chg)[WORDS], uint32_t& cnt) {
+    const int trips = P.tm_trips_v;
+    const int full = P.n / t.nthr;
+    const uint32_t step = (uint32_t)t.nthr * (uint32_t)sizeof(VecT<WORDS>);
+    uint32_t xa = t.sa_x + (uint32_t)t.tid * (uint32_t)sizeof(VecT<WORDS>);
+    uint32_t ta = t.ta_v;
+    LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
+    cnt = 0u;
+    uint32_t a[DV];
+    tm_ld<DV>(ta, a);
+    auto trip = [&](bool more, bool valid) {
+        tm_wait_ld<DV>(a);
+        VecT<WORDS> tw[DV], xi;
+        if (valid) {
+            xi = lds_vec_ordered<WORDS>(xa);   // own state: its address does not derive from a post-barrier load
+#pragma unroll
+            for (int j = 0; j < DV; j++) tw[j] = lds_vec<WORDS>(a[j]);
+        }
+        ta += DV;
+        if (more) tm_ld<DV>(ta, a);
+        if (valid) {
+            VecT<WORDS> xn = xi;
+#pragma unroll
+            for (int j = 0; j < DV; j++) LDPC_FORW xn.a[w] &= tw[j].a[w];
+            sts_vec<WORDS>(xa, xn);
+            LDPC_FORW {
+                any[w] |= xn.a[w];
+                chg[w] |= xi.a[w] ^ xn.a[w];
+                cnt += __popc(MASKED ? (xn.a[w] & mask[w]) : xn.a[w]);
+            }
+        }
+        xa += step;
+    };
+#pragma unroll 2
+    for (int tr = 0; tr < full; tr++) trip(tr + 1 < trips, true);
+    if (full < trips) trip(false, full * t.nthr + t.tid < P.n);
+}
+
+// every thread writes the gather addresses of its nodes into its tensor-memory columns (once per launch)
+template <int WORDS, int DV, int DC>
+__device__ __forceinline__ void tm_fill_lists(const E1Params& P, TeamCtx& t, uint32_t tbase) {
+    const int wcta = (int)(threadIdx.x >> 5);
+    const uint32_t ta0 = tbase + ((uint32_t)(32 * (wcta & 3)) << 16) + (uint32_t)((wcta >> 2) * P.tm_cpw);
+    t.ta_c = ta0;
+    t.ta_v = ta0 + (uint32_t)(P.tm_trips_c * DC);
+    for (int tr = 0; tr < P.tm_trips_c; tr++) {
+        const int c = tr * t.nthr + t.tid;
+        uint32_t a[DC];
+#pragma unroll
+        for (int j = 0; j < DC; j++) a[j] = t.sa_x;
+        if (c < P.m) gather_addrs<DC, true, false>(P, P.c2v, P.m_pad, c, t.sa_x, (uint32_t)sizeof(VecT<WORDS>), a);
+        tm_st<DC>(t.ta_c + (uint32_t)(tr * DC), a);
+    }
+    for (int tr = 0; tr < P.tm_trips_v; tr++) {
+        const int i = tr * t.nthr + t.tid;
+        uint32_t a[DV];
+#pragma unroll
+        for (int j = 0; j < DV; j++) a[j] = t.sa_t;
+        if (i < P.n) gather_addrs<DV, true, false>(P, P.v2c, P.n_pad, i, t.sa_t, (uint32_t)sizeof(VecT<WORDS>), a);
+        tm_st<DV>(t.ta_v + (uint32_t)(tr * DV), a);
+    }
+    tm_wait_st();
 }
 
 __device__ __forceinline__ void red_add(unsigned long long* p, unsigned long long v) {
@@ -490,7 +645,7 @@ __device__ __forceinline__ void stage_v2c_resident(const E1Params& P, unsigned c
 
 // Decode one frame group for the Monte-Carlo path.  MASKED pass: erasure sums restricted to `mask`.
 // Returns physical iterations executed; outputs the team-uniform masks / counts by reference.
-template <int WORDS, int DV, int DC, bool MASKED>
+template <int WORDS, int DV, int DC, bool MASKED, bool TM = false>
 __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, const BecParams& bp, uint32_t point,
                                         unsigned long long q0, const uint32_t (&valid)[WORDS],
                                         const uint32_t (&mask)[WORDS], const uint16_t* s_c2v, const uint16_t* s_v2c,
@@ -513,10 +668,16 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
         LDPC_FORW { r |= running[w]; pc += __popc(running[w]); }
         if (r == 0u) break;
         exec_sum += pc;
-        check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
-        team_sync(t);
         uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-        mc_var_phase<WORDS, DV, DC, MASKED>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(t.sm + P.sm_vres), x, two, mask, a2, c2, cnt);
+        if constexpr (TM) {
+            check_phase_tm<WORDS, DC>(P, t);
+            team_sync(t);
+            var_phase_tm<WORDS, DV, MASKED>(P, t, mask, a2, c2, cnt);
+        } else {
+            check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
+            team_sync(t);
+            mc_var_phase<WORDS, DV, DC, MASKED>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(t.sm + P.sm_vres), x, two, mask, a2, c2, cnt);
+        }
         LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
         team_reduce<2 * WORDS>(t, oc, cnt);
         if (t.tid == 0) hbuf[it + 1] = cnt;
@@ -530,14 +691,15 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
     return it;
 }
 
-template <int WORDS, int DV, int DC>
+template <int WORDS, int DV, int DC, bool TM = false>
 __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __grid_constant__ E1Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t tm_slot;
     uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
     uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
 
     // stage the graph once per CTA (16-byte vectors; arrays are padded to 16 bytes on the host)
-    if (!P.ens) {
+    if (!P.ens && !TM) {
         const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
         const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
         const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
@@ -567,6 +729,11 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     // scratch map: [0 .. 32*(2*WORDS+1))  reduce area ; then [work slot (2 words)] ; then rf[32*WORDS]
     uint32_t* work_slot = t.scr + 32 * (2 * WORDS + 1);
     uint32_t* rf = work_slot + 2;
+    uint32_t tm_base = 0;
+    if constexpr (TM) {   // socket lists -> tensor memory (e1_tmem.cuh)
+        tm_base = tm_alloc_all(&tm_slot);
+        tm_fill_lists<WORDS, DV, DC>(P, t, tm_base);
+    }
 
     const unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
     const int W = 32 * WORDS;
@@ -637,8 +804,8 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
 
         uint32_t any[WORDS], cnt;
         unsigned long long exec_sum;
-        int iters = mc_group<WORDS, DV, DC, false>(P, t, bp, point, q0, valid, valid, s_c2v, s_v2c, x, two, hbuf,
-                                                   any, cnt, exec_sum);
+        int iters = mc_group<WORDS, DV, DC, false, TM>(P, t, bp, point, q0, valid, valid, s_c2v, s_v2c, x, two, hbuf,
+                                                       any, cnt, exec_sum);
         unsigned long long* C = P.counters + (size_t)point * stride;
         unsigned long long phys = (unsigned long long)iters * W;
         uint32_t nvalid = 0;
@@ -677,8 +844,8 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
             if (kall != 0u) {
                 // mixed group: re-decode with the erasure sums restricted to the counted frames
                 unsigned long long e2;
-                iters = mc_group<WORDS, DV, DC, true>(P, t, bp, point, q0, valid, K, s_c2v, s_v2c, x, two, hbuf,
-                                                      any, cnt, e2);
+                iters = mc_group<WORDS, DV, DC, true, TM>(P, t, bp, point, q0, valid, K, s_c2v, s_v2c, x, two, hbuf,
+                                                          any, cnt, e2);
                 phys += (unsigned long long)iters * W;
                 second = true;
             }
@@ -700,6 +867,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         }
         team_sync(t);  // hbuf is rewritten by the next group
     }
+    if constexpr (TM) tm_free_all(tm_base);
 }
 
 // tail[b] is added to every bin >= b:  bins after a group's last physical iteration keep its residual

@@ -48,13 +48,14 @@ struct StageParams {
     unsigned long long* stop_hist;        // optional [npoints][cap+1]: frames by executed-iteration count
 };
 
-template <int WORDS, int DV, int DC>
+template <int WORDS, int DV, int DC, bool TM = false>
 __global__ void __launch_bounds__(e1_threads(WORDS), 1)
 e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t tm_slot;
     uint16_t* s_c2v = reinterpret_cast<uint16_t*>(smem + P.sm_c2v);
     uint16_t* s_v2c = reinterpret_cast<uint16_t*>(smem + P.sm_v2c);
-    {
+    if (!TM) {
         const int dc = DC ? DC : P.dc, dv = DV ? DV : P.dv;
         const int nc = dc * P.m_pad / 8, nv = dv * P.n_pad / 8;
         const uint4* g0 = reinterpret_cast<const uint4*>(P.c2v);
@@ -83,6 +84,11 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
     uint32_t* work_slot = t.scr + 32 * (2 * WORDS + 1);
+    uint32_t tm_base = 0;
+    if constexpr (TM) {   // socket lists -> tensor memory (e1_tmem.cuh)
+        tm_base = tm_alloc_all(&tm_slot);
+        tm_fill_lists<WORDS, DV, DC>(P, t, tm_base);
+    }
 
     constexpr int W = 32 * WORDS;
     const int stride = raw_stride(P.cap);
@@ -184,10 +190,16 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             LDPC_FORW { r |= running[w]; pc += __popc(running[w]); }
             if (r == 0u) break;
             exec_sum += pc;
-            check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
-            team_sync(t);
             uint32_t oc[2 * WORDS], a2[WORDS], c2[WORDS];
-            mc_var_phase<WORDS, DV, DC, false>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(smem + P.sm_vres), x, two, valid, a2, c2, cnt);
+            if constexpr (TM) {
+                check_phase_tm<WORDS, DC>(P, t);
+                team_sync(t);
+                var_phase_tm<WORDS, DV, false>(P, t, valid, a2, c2, cnt);
+            } else {
+                check_phase<WORDS, DV, DC, false>(P, t, s_c2v, x, two, nullptr, nullptr);
+                team_sync(t);
+                mc_var_phase<WORDS, DV, DC, false>(P, t, s_v2c, reinterpret_cast<const uint16_t*>(smem + P.sm_vres), x, two, valid, a2, c2, cnt);
+            }
             LDPC_FORW { oc[w] = a2[w]; oc[WORDS + w] = c2[w]; }
             team_reduce<2 * WORDS>(t, oc, cnt);
             if (t.tid == 0) hbuf[age - lo + 1] = cnt;
@@ -278,6 +290,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
         }
         team_sync(t);   // shared state is rewritten by the next group
     }
+    if constexpr (TM) tm_free_all(tm_base);
 }
 
 }  // namespace ldpc

@@ -61,6 +61,7 @@ struct E1Config {
     uint32_t smem = 0;
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
     int v2c_res = 0; uint32_t sm_vres = 0;   // v2c_global: resident part of the variable-side lists
+    bool tm = false; int tm_cpw = 0, tm_trips_c = 0, tm_trips_v = 0;   // socket lists in tensor memory (e1_tmem.cuh)
 };
 
 struct StagePlan {
@@ -124,8 +125,58 @@ static int tuning_env(const char* name) {
     return s ? atoi(s) : 0;
 }
 
+// Plan with the socket lists in tensor memory (e1_tmem.cuh): shared memory holds state only; every thread's gather
+// addresses must fit its warp's share of the 512 TMEM columns (4 lane quarters x 512 columns x 32 lanes).
+static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg) {
+    if (!((g->dv == 3 && g->dc == 6) || (g->dv == 4 && g->dc == 8))) return false;   // degree pairs the kernels are specialised for
+    if (g->n > 65535 || tuning_env("LDPC_B200_TMEM") == 2) return false;
+    const uint32_t limit = (uint32_t)g->smem_optin;
+    const int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
+    const int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
+    const int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
+    const int cand[3] = {4, 2, 1};
+    for (int ci = 0; ci < 3; ci++) {
+        const int words = cand[ci];
+        if (want_words && words != want_words) continue;
+        E1Config c;
+        uint32_t off = 0;
+        c.sm_x = off; off += align_up((uint32_t)g->n * 4 * words, 16);
+        c.sm_t = off; off += align_up((uint32_t)g->m * 4 * words, 16);
+        c.sm_v = off; c.sm_p = off;
+        c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
+        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words + 8) * 4, 16);
+        const uint32_t tb = off;
+        if (tb > limit) continue;
+        const int max_warps = e1_threads(words) / 32;
+        const int fit = (int)(limit / tb);
+        // most warps first; among equals the fewest teams (wider teams amortise the per-group work better)
+        int best_teams = 0, best_tw = 0;
+        for (int teams = std::min(fit, std::min(max_warps, 15)); teams >= 1; teams--) {
+            if (want_teams && teams != std::min(want_teams, fit)) continue;
+            for (int tw = max_warps / teams; tw >= 1; tw--) {
+                if (want_tw && tw != want_tw) continue;
+                const int nthr = tw * 32, wpq = (teams * tw + 3) / 4;
+                const int tc = (g->m + nthr - 1) / nthr, tv = (g->n + nthr - 1) / nthr;
+                if ((tc * g->dc + tv * g->dv) * wpq > 512) continue;
+                if (teams * tw > best_teams * best_tw) { best_teams = teams; best_tw = tw; }
+                break;
+            }
+        }
+        if (!best_teams) continue;
+        const int nthr = best_tw * 32;
+        c.words = words; c.teams = best_teams; c.team_warps = best_tw; c.values = false; c.v2c_global = false;
+        c.sm_c2v = 0; c.sm_v2c = 0; c.sm_team0 = 0; c.sm_team_stride = tb; c.smem = tb * best_teams;
+        c.tm = true; c.tm_trips_c = (g->m + nthr - 1) / nthr; c.tm_trips_v = (g->n + nthr - 1) / nthr;
+        c.tm_cpw = c.tm_trips_c * g->dc + c.tm_trips_v * g->dv;
+        cfg = c;
+        return true;
+    }
+    return false;
+}
+
 // Shared-memory plan for E1.  Returns false if even one W=32 team does not fit.
 static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode, E1Config& cfg) {
+    if (!values && !decode && plan_e1_tm(g, cap, cfg)) return true;
     const uint32_t limit = (uint32_t)g->smem_optin;
     const uint32_t graph_bytes = align_up((uint32_t)g->dc * g->m_pad * 2, 16) + align_up((uint32_t)g->dv * g->n_pad * 2, 16);
     if (g->n > 65535) return false;
@@ -205,6 +256,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
     P.cap = cap;
+    P.tm = c.tm ? 1 : 0; P.tm_cpw = c.tm_cpw; P.tm_trips_c = c.tm_trips_c; P.tm_trips_v = c.tm_trips_v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,6 +392,8 @@ static cudaError_t launch_mc_words(const E1Params& P, int grid, int block, uint3
         kern<<<grid, block, smem, st>>>(P);
         return cudaGetLastError();
     };
+    if (P.tm && P.dv == 3 && P.dc == 6) return go(e1_mc_kernel<WORDS, 3, 6, true>);
+    if (P.tm && P.dv == 4 && P.dc == 8) return go(e1_mc_kernel<WORDS, 4, 8, true>);
     if (P.dv == 3 && P.dc == 6) return go(e1_mc_kernel<WORDS, 3, 6>);
     if (P.dv == 4 && P.dc == 8) return go(e1_mc_kernel<WORDS, 4, 8>);
     return go(e1_mc_kernel<WORDS, 0, 0>);

@@ -198,37 +198,75 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
 
 
 def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128, stop_rule_graphs=4096,
-                   wall_clock_limit=43000, gen_mode=2):
+                   wall_clock_limit=43000, gen_mode=2, exact_stop=True, max_block_errors=200):
     """Ensemble Monte-Carlo (parallel_simulator_expurgated.py:169-285): a fresh random graph per frame group.
 
     gen_mode 2 (default): graph G is built by the kernel itself in shared memory (host twin:
     generate_graph_indexed(n, dv, dc, seed, G)); gen_mode 0/1: generate_graph(n, dv, dc, seed*1000003 + G, gen_mode) on
     a pool of host threads.  Graph G decodes the global frames [G*F, G*F + frames_per_graph), F = frames_per_graph
-    rounded up to 128 (ldpc_b200_mc_run_ensemble); the 200-block-error rule (:200) is checked every
-    `stop_rule_graphs` graphs."""
-    if gen_mode == 2 and n * dv > 65535:
-        gen_mode = 1
+    rounded up to 128 (ldpc_b200_mc_run_ensemble).
+
+    Stop rule (:200 `while block_error<200 and i<num_tests`): checked every `stop_rule_graphs` graphs; the batch
+    that crosses the limit is then truncated by bisection on the deterministic counters -- to the graph of the
+    200th counted failure and, inside that graph, to the frame of the 200th failure (exact ordered truncation;
+    frames are keyed by their global index so a shorter run of the same graph decodes the same frames)."""
     eps = parameter_set["BEC"]
     num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
     n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]
     if parameter_set.get("optimal"):
         raise NotImplementedError("ML decoding is outside the accelerated hot path")
+    if gen_mode == 2 and n * dv > 65535:     # the in-kernel generator sorts 16-bit socket ids
+        gen_mode = 1
     seed = int(parameter_set["seed"])
     expurgation = int(parameter_set.get("expurgation", -1))
     k = int(n * (dc - dv) / dc)
     start = time.time()
+    its = iterations
+    fpg = int(frames_per_graph)
+    stride = (fpg + 127) // 128 * 128
+
+    def ens(first_graph, graphs, frames=fpg):
+        return api.mc_run_ensemble(n, dv, dc, [eps], seed, graphs, iterations, frames_per_graph=frames,
+                                   graph_seed=seed, gen_mode=gen_mode, first_graph=first_graph,
+                                   expurgation=expurgation, device=device, frame_stride=stride)[0]
+
     total = np.zeros(iterations + 6, dtype=np.uint64)
     done, gi = 0, 0
-    while int(total[iterations + 1]) < 200 and done < num_tests and time.time() - start < wall_clock_limit:   # :200
-        # whole graphs only: num_tests is rounded up to a multiple of frames_per_graph (the CSV reports the actual count)
-        graphs = min(stop_rule_graphs, (num_tests - done + frames_per_graph - 1) // frames_per_graph)
-        total += api.mc_run_ensemble(n, dv, dc, [eps], seed, graphs, iterations, frames_per_graph=frames_per_graph,
-                                     graph_seed=seed, gen_mode=gen_mode, first_graph=gi, expurgation=expurgation,
-                                     device=device)[0]
-        done += graphs * frames_per_graph
+    while int(total[its + 1]) < max_block_errors and done < num_tests and time.time() - start < wall_clock_limit:   # :200
+        # whole graphs, except the last one of the run: num_tests frames in total
+        graphs = min(stop_rule_graphs, (num_tests - done + fpg - 1) // fpg)
+        last_frames = min(fpg, num_tests - done - (graphs - 1) * fpg)
+        part = ens(gi, graphs) if last_frames == fpg else ens(gi, graphs - 1) + ens(gi + graphs - 1, 1, last_frames) \
+            if graphs > 1 else ens(gi, 1, last_frames)
+        frames_here = (graphs - 1) * fpg + last_frames
+        if exact_stop and int(total[its + 1]) + int(part[its + 1]) >= max_block_errors:
+            need = max_block_errors - int(total[its + 1])
+            lo, hi = 1, graphs           # smallest G with block_errors(first G graphs of this batch) >= need
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if int(ens(gi, mid)[its + 1]) >= need:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            before = ens(gi, lo - 1) if lo > 1 else np.zeros_like(total)
+            need -= int(before[its + 1])
+            top = last_frames if lo == graphs else fpg
+            a, b = 1, top                # smallest L with block_errors(first L frames of graph gi+lo-1) >= need
+            while a < b:
+                mid = (a + b) // 2
+                if int(ens(gi + lo - 1, 1, mid)[its + 1]) >= need:
+                    b = mid
+                else:
+                    a = mid + 1
+            part = before + ens(gi + lo - 1, 1, a)
+            frames_here = (lo - 1) * fpg + a
+            graphs = lo
+        total += part
+        done += frames_here
         gi += graphs
     res = _finish("regular_code_expurgated=" + str(expurgation), eps, n, k, dv, dc, iterations, total, write_csv)
     res["graphs"] = gi
+    res.update(validation_overlays(res, eps, n, dv, dc))
     return res
 
 
