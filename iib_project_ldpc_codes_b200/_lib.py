@@ -81,8 +81,8 @@ def load() -> ct.CDLL:
                                      ct.c_int, P_U64, ct.POINTER(McStats)]
     lib.ldpc_b200_mc_run_ensemble.restype = ct.c_int
     lib.ldpc_b200_mc_run_ensemble.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_uint64, ct.c_int, ct.c_uint64,
-                                              ct.c_uint64, ct.c_uint32, P_F64, ct.c_int, ct.c_uint64, ct.c_int, ct.c_int,
-                                              P_U64, ct.POINTER(McStats)]
+                                              ct.c_uint64, ct.c_uint32, ct.c_uint32, P_F64, ct.c_int, ct.c_uint64, ct.c_int,
+                                              ct.c_int, P_U64, ct.POINTER(McStats)]
     lib.ldpc_b200_mc_launch.restype = ct.c_int
     lib.ldpc_b200_mc_launch.argtypes = [ct.c_void_p, P_F64, ct.c_int, ct.c_uint64, ct.c_uint64, ct.c_uint64, ct.c_int,
                                         ct.c_int, ct.c_void_p, ct.c_void_p]

@@ -182,15 +182,15 @@ class Graph:
 
 
 def mc_run_ensemble(n, dv, dc, eps, seed, num_graphs, iterations, frames_per_graph=128, graph_seed=1, gen_mode=1,
-                    first_graph=0, expurgation=-1, device=0, return_stats=False):
+                    first_graph=0, expurgation=-1, device=0, return_stats=False, frame_stride=0):
     """Ensemble Monte-Carlo: graph G = generate_graph(n, dv, dc, graph_seed*1000003 + G, gen_mode) decodes the
-    global frames [G*F, G*F + frames_per_graph), F = frames_per_graph rounded up to 128."""
+    global frames [G*F, G*F + frames_per_graph), F = frame_stride (0: frames_per_graph rounded up to 128)."""
     lib = _lib.load()
     eps = np.ascontiguousarray(np.atleast_1d(eps), dtype=np.float64)
     out = np.zeros((len(eps), counters_len(iterations)), dtype=np.uint64)
     st = McStats()
     check(lib.ldpc_b200_mc_run_ensemble(device, n, dv, dc, graph_seed, gen_mode, first_graph, num_graphs,
-                                        frames_per_graph, ptr(eps, P_F64), len(eps), seed, iterations, expurgation,
+                                        frames_per_graph, frame_stride, ptr(eps, P_F64), len(eps), seed, iterations, expurgation,
                                         ptr(out, P_U64), ct.byref(st)))
     return (out, st.as_dict()) if return_stats else out
 

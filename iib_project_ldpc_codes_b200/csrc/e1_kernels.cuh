@@ -41,6 +41,9 @@ constexpr int E1_MAX_THREADS = 512;
 #ifndef LDPC_VAR_UNROLL_VG
 #define LDPC_VAR_UNROLL_VG 4
 #endif
+#ifndef LDPC_TM_PIPE
+#define LDPC_TM_PIPE 1   // software-pipeline the tensor-memory phases two trips deep (when the registers allow)
+#endif
 constexpr int kCheckUnroll = LDPC_CHECK_UNROLL, kVarUnroll = LDPC_VAR_UNROLL, kVarUnrollVG = LDPC_VAR_UNROLL_VG;
 // one word per node (W = 32) needs few registers: run 32 warps per SM to hide shared-memory latency
 __host__ __device__ constexpr int e1_threads(int words) { return words == 1 ? 1024 : (words == 4 ? LDPC_W128_THREADS : LDPC_W64_THREADS); }
@@ -91,6 +94,7 @@ struct E1Params {
     // socket lists in tensor memory (e1_tmem.cuh): ready-made gather addresses per thread, no lists in shared memory
     int tm;                                 // 1: on (kernels instantiated with TM = true)
     int tm_cpw, tm_trips_c, tm_trips_v;     // columns per warp, check / variable trips per thread
+    int tm_full_c, tm_full_v;               // trips in which every thread of a team has a node (m / T, n / T)
     // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
     // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
     // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c
@@ -422,72 +426,117 @@ __device__ __forceinline__ VecT<WORDS> check_two(const VecT<WORDS> (&v)[DC]) {
     return tw;
 }
 
-// One trip = one node per thread.  Order inside a trip: wait for this trip's addresses, issue its gathers, request the
-// next trip's addresses into the same registers (the gathers have read them), then combine and store.
+// One trip = one node per thread.  The trips are software-pipelined two deep: the gathers of trip k+1 are issued
+// (and the addresses of trip k+2 requested from tensor memory, into the registers those gathers have just read)
+// BEFORE trip k is combined and stored, so every warp keeps two nodes' worth of shared-memory loads in flight --
+// with 24 warps per SM the gather latency was the top stall (ncu short-scoreboard).  No hazard: within a phase the
+// array gathered from is never the array stored to, and a thread's own x vectors of different trips are distinct.
+// full = trips in which every thread of the team has a node (host-computed: no integer division per phase).
 template <int WORDS, int DC>
 __device__ __forceinline__ void check_phase_tm(const E1Params& P, const TeamCtx& t) {
-    const int trips = P.tm_trips_c;
-    const int full = P.m / t.nthr;          // trips in which every thread of the team has a check
+    const int T = P.tm_trips_c, F = P.tm_full_c;
     const uint32_t step = (uint32_t)t.nthr * (uint32_t)sizeof(VecT<WORDS>);
     uint32_t dst = t.sa_t + (uint32_t)t.tid * (uint32_t)sizeof(VecT<WORDS>);
     uint32_t ta = t.ta_c;
     uint32_t a[DC];
     tm_ld<DC>(ta, a);
-    auto trip = [&](bool more, bool valid) {
+    auto issue = [&](VecT<WORDS> (&v)[DC], bool more) {
         tm_wait_ld<DC>(a);
-        VecT<WORDS> v[DC];
-        if (valid) {
 #pragma unroll
-            for (int j = 0; j < DC; j++) v[j] = lds_vec<WORDS>(a[j]);
-        }
+        for (int j = 0; j < DC; j++) v[j] = lds_vec<WORDS>(a[j]);
         ta += DC;
         if (more) tm_ld<DC>(ta, a);   // warp-uniform
-        if (valid) sts_vec<WORDS>(dst, check_two<WORDS, DC>(v));
+    };
+    auto finish = [&](const VecT<WORDS> (&v)[DC]) {
+        sts_vec<WORDS>(dst, check_two<WORDS, DC>(v));
         dst += step;
     };
+    VecT<WORDS> v0[DC], v1[DC];
+    constexpr bool PIPE = LDPC_TM_PIPE && DC * WORDS <= 24;   // two sets of gathered vectors must fit the register budget
+    if (PIPE && F > 0) {
+        issue(v0, 1 < T);
+        int k = 0;
+#pragma unroll 1
+        for (; k + 2 < F; k += 2) {
+            issue(v1, true); finish(v0);          // trips k+1 and k+2 are full trips: a further trip follows each
+            issue(v0, k + 3 < T); finish(v1);
+        }
+        if (k + 1 < F) { issue(v1, k + 2 < T); finish(v0); finish(v1); }
+        else finish(v0);
+    } else {
 #pragma unroll 2
-    for (int tr = 0; tr < full; tr++) trip(tr + 1 < trips, true);
-    if (full < trips) trip(false, full * t.nthr + t.tid < P.m);   // last trip: some lanes have no check
+        for (int k = 0; k < F; k++) { issue(v0, k + 1 < T); finish(v0); }
+    }
+    if (F < T) {   // last trip: only the first lanes of the team have a check (the others' columns hold a harmless address)
+        tm_wait_ld<DC>(a);
+        if (F * t.nthr + t.tid < P.m) {
+#pragma unroll
+            for (int j = 0; j < DC; j++) v0[j] = lds_vec<WORDS>(a[j]);
+            finish(v0);
+        }
+    }
 }
 
 template <int WORDS, int DV, bool MASKED>
 __device__ __forceinline__ void var_phase_tm(const E1Params& P, const TeamCtx& t, const uint32_t (&mask)[WORDS],
                                              uint32_t (&any)[WORDS], uint32_t (&chg)[WORDS], uint32_t& cnt) {
-    const int trips = P.tm_trips_v;
-    const int full = P.n / t.nthr;
+    const int T = P.tm_trips_v, F = P.tm_full_v;
     const uint32_t step = (uint32_t)t.nthr * (uint32_t)sizeof(VecT<WORDS>);
-    uint32_t xa = t.sa_x + (uint32_t)t.tid * (uint32_t)sizeof(VecT<WORDS>);
+    uint32_t xa = t.sa_x + (uint32_t)t.tid * (uint32_t)sizeof(VecT<WORDS>);   // own state vector of the trip being issued
+    uint32_t xs = xa;                                                          // ... of the trip being finished
     uint32_t ta = t.ta_v;
     LDPC_FORW { any[w] = 0u; chg[w] = 0u; }
     cnt = 0u;
     uint32_t a[DV];
     tm_ld<DV>(ta, a);
-    auto trip = [&](bool more, bool valid) {
+    // v[0 .. DV-1] = gathered `two` vectors, v[DV] = own state (its address does not derive from a post-barrier load:
+    // ordered load)
+    auto issue = [&](VecT<WORDS> (&v)[DV + 1], bool more) {
         tm_wait_ld<DV>(a);
-        VecT<WORDS> tw[DV], xi;
-        if (valid) {
-            xi = lds_vec_ordered<WORDS>(xa);   // own state: its address does not derive from a post-barrier load
+        v[DV] = lds_vec_ordered<WORDS>(xa);
 #pragma unroll
-            for (int j = 0; j < DV; j++) tw[j] = lds_vec<WORDS>(a[j]);
-        }
+        for (int j = 0; j < DV; j++) v[j] = lds_vec<WORDS>(a[j]);
+        xa += step;
         ta += DV;
         if (more) tm_ld<DV>(ta, a);
-        if (valid) {
-            VecT<WORDS> xn = xi;
-#pragma unroll
-            for (int j = 0; j < DV; j++) LDPC_FORW xn.a[w] &= tw[j].a[w];
-            sts_vec<WORDS>(xa, xn);
-            LDPC_FORW {
-                any[w] |= xn.a[w];
-                chg[w] |= xi.a[w] ^ xn.a[w];
-                cnt += __popc(MASKED ? (xn.a[w] & mask[w]) : xn.a[w]);
-            }
-        }
-        xa += step;
     };
+    auto finish = [&](const VecT<WORDS> (&v)[DV + 1]) {
+        VecT<WORDS> xn = v[DV];
+#pragma unroll
+        for (int j = 0; j < DV; j++) LDPC_FORW xn.a[w] &= v[j].a[w];
+        sts_vec<WORDS>(xs, xn);
+        xs += step;
+        LDPC_FORW {
+            any[w] |= xn.a[w];
+            chg[w] |= v[DV].a[w] ^ xn.a[w];
+            cnt += __popc(MASKED ? (xn.a[w] & mask[w]) : xn.a[w]);
+        }
+    };
+    VecT<WORDS> v0[DV + 1], v1[DV + 1];
+    constexpr bool PIPE = LDPC_TM_PIPE && (DV + 1) * WORDS <= 24;
+    if (PIPE && F > 0) {
+        issue(v0, 1 < T);
+        int k = 0;
+#pragma unroll 1
+        for (; k + 2 < F; k += 2) {
+            issue(v1, true); finish(v0);
+            issue(v0, k + 3 < T); finish(v1);
+        }
+        if (k + 1 < F) { issue(v1, k + 2 < T); finish(v0); finish(v1); }
+        else finish(v0);
+    } else {
 #pragma unroll 2
-    for (int tr = 0; tr < full; tr++) trip(tr + 1 < trips, true);
-    if (full < trips) trip(false, full * t.nthr + t.tid < P.n);
+        for (int k = 0; k < F; k++) { issue(v0, k + 1 < T); finish(v0); }
+    }
+    if (F < T) {
+        tm_wait_ld<DV>(a);
+        if (F * t.nthr + t.tid < P.n) {
+            v0[DV] = lds_vec_ordered<WORDS>(xa);
+#pragma unroll
+            for (int j = 0; j < DV; j++) v0[j] = lds_vec<WORDS>(a[j]);
+            finish(v0);
+        }
+    }
 }
 
 // every thread writes the gather addresses of its nodes into its tensor-memory columns (once per launch)

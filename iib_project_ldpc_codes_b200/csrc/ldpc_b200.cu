@@ -257,6 +257,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
     P.cap = cap;
     P.tm = c.tm ? 1 : 0; P.tm_cpw = c.tm_cpw; P.tm_trips_c = c.tm_trips_c; P.tm_trips_v = c.tm_trips_v;
+    P.tm_full_c = g->m / (c.team_warps * 32); P.tm_full_v = g->n / (c.team_warps * 32);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -142,9 +142,81 @@ def density_evolution_overlay(average_errors, eps, dv, dc, first=8):
     return {"iterations_compared": int(k), "max_abs_deviation": float(dev.max()), "de_curve": de.tolist()}
 
 
+def _de_below_threshold(erasure_prob, dv, dc, iterations=100000, tolerance=1e-6):
+    """test_de_threshold.py:7-15: does the density-evolution recursion of the (dv,dc) ensemble die out?"""
+    prob = 1.0
+    for _ in range(iterations):
+        last = prob
+        prob = erasure_prob * (1.0 - (1.0 - last) ** (dc - 1)) ** (dv - 1)
+        if prob < tolerance * 1e-3 or last - prob < 1e-16 * max(prob, 1e-300):   # decided: vanished / reached its fixed point
+            break
+    return prob < tolerance
+
+
+def calc_threshold(dv, dc):
+    """BP threshold of the (dv,dc)-regular ensemble on the BEC by bisection (restates test_de_threshold.py:17-28;
+    (3,6) -> 0.429440, (4,8) -> 0.383447)."""
+    lo, hi = 0.0, 1.0
+    while hi - lo > 1e-9:
+        mid = 0.5 * (lo + hi)
+        if _de_below_threshold(mid, dv, dc):
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def calculate_threshold_y(threshold_erasure, dv, dc):
+    """finite_length_scaling_calculation.py:9-16: check-to-variable erasure probability at the critical point."""
+    previous, value = 0.0, 1.0
+    while abs(value - previous) > 1e-6:
+        previous = value
+        value = 1.0 - (1.0 - threshold_erasure * value ** (dv - 1)) ** (dc - 1)
+    return value
+
+
+def calculate_alpha(threshold, dv, dc):
+    """finite_length_scaling_calculation.py:18-21: the scaling parameter alpha of the waterfall."""
+    y = calculate_threshold_y(threshold, dv, dc)
+    x = threshold * y ** (dv - 1)
+    return threshold * np.sqrt(((dv - 1) / dv) * (1.0 / x - 1.0 / y))
+
+
+_threshold_cache = {}
+
+
+def scaling_law_block_error(n, dv, dc, erasure_prob):
+    """P_B ~ Q(sqrt(n) (eps* - eps) / alpha)  (finite_length_scaling_calculation.py:23-29,38-44, without the
+    n^(-2/3) shift, as the reference evaluates it)."""
+    from math import erfc, sqrt
+    if (dv, dc) not in _threshold_cache:
+        th = calc_threshold(dv, dc)
+        _threshold_cache[(dv, dc)] = (th, float(calculate_alpha(th, dv, dc)))
+    th, alpha = _threshold_cache[(dv, dc)]
+    z = sqrt(n) * (th - erasure_prob)
+    return 0.5 * erfc(z / alpha / sqrt(2.0)), th, alpha
+
+
+def validation_overlays(res, eps, n, dv, dc):
+    """The checks the reference did by eye, attached to every run's result: mean erasure curve against modified
+    density evolution (tools/plotting.py:86), and the measured block error rate against the finite-length scaling
+    law around the BP threshold (finite_length_scaling_calculation.py:38-44, test_de_threshold.py:17-28)."""
+    pb, th, alpha = scaling_law_block_error(n, dv, dc, eps)
+    return {"density_evolution": density_evolution_overlay(res["average_errors"], eps, dv, dc),
+            "bp_threshold": th,
+            "scaling_law": {"alpha": alpha, "predicted_block_error": pb, "measured_block_error": res["block_error"],
+                            "z": float(np.sqrt(n) * (th - eps))}}
+
+
 def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=None, stop_rule_batch=None,
-                              wall_clock_limit=42000, exact_stop=True, max_block_errors=200):
-    """Fixed-code Monte-Carlo (parallel_simulator_expurgated.py:287-414)."""
+                              wall_clock_limit=42000, exact_stop=True, max_block_errors=200,
+                              dense_code_limit_bytes=1 << 27):
+    """Fixed-code Monte-Carlo (parallel_simulator_expurgated.py:287-414).
+
+    Code cache (:303-348): `check_code_no_*`, `variable_code_no_*` (int32 lookups) and `code_no_*` (the dense bool
+    parity-check matrix [(n-k), n]) in base_directory/parity_checks, the three files the reference looks for -- a
+    later reference run finds all of them and decodes the same code.  The dense file is only needed by the
+    reference (the GPU path never reads it); it is written when it is at most `dense_code_limit_bytes`."""
     eps = parameter_set["BEC"]
     num_tests, iterations = parameter_set["num_tests"], parameter_set["iterations"]
     n, dv, dc = parameter_set["n"], parameter_set["dv"], parameter_set["dc"]
@@ -158,13 +230,18 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
     tag = str(filenumber) + "_n_" + str(n) + "_dv_" + str(dv) + "_dc_" + str(dc) + ".npy"
     check_path = os.path.join(pdir, "check_code_no_" + tag)
     var_path = os.path.join(pdir, "variable_code_no_" + tag)
-    if os.path.exists(check_path) and os.path.exists(var_path):          # :303-319 (the dense code_no_* file is not needed)
+    code_path = os.path.join(pdir, "code_no_" + tag)
+    if os.path.exists(check_path) and os.path.exists(var_path):          # :303-319 (the GPU path needs the lookups only)
         check_lookup = np.load(check_path)
         variable_lookup = np.load(var_path)
     else:                                                                 # :322-348
         variable_lookup, check_lookup = api.generate_graph(n, dv, dc, seed=int(filenumber), mode=1)
-        np.save(check_path, check_lookup.ravel())
-        np.save(var_path, variable_lookup.ravel())
+        np.save(check_path, check_lookup.ravel().astype(np.int32))
+        np.save(var_path, variable_lookup.ravel().astype(np.int32))
+    if not os.path.exists(code_path) and (n - k) * n <= dense_code_limit_bytes:   # :342-344, for the reference's loader
+        H = np.zeros((n - k, n), dtype=bool)
+        H[np.repeat(np.arange(n - k), dc), np.asarray(check_lookup).reshape(-1)] = True
+        np.save(code_path, H)
     g = api.Graph(np.asarray(variable_lookup).reshape(n, dv), np.asarray(check_lookup).reshape(n - k, dc), device=device)
     seed = int(filenumber) if run_seed is None else run_seed
     total = np.zeros(iterations + 6, dtype=np.uint64)
@@ -193,7 +270,7 @@ def run_simulation_fixed_ldpc(parameter_set, write_csv=True, device=0, run_seed=
         done += cnt
     g.close()
     res = _finish("regular_code_code_number=" + str(filenumber), eps, n, k, dv, dc, iterations, total, write_csv)
-    res["density_evolution"] = density_evolution_overlay(res["average_errors"], eps, dv, dc)
+    res.update(validation_overlays(res, eps, n, dv, dc))
     return res
 
 
@@ -236,8 +313,12 @@ def run_simulation(parameter_set, write_csv=True, device=0, frames_per_graph=128
         # whole graphs, except the last one of the run: num_tests frames in total
         graphs = min(stop_rule_graphs, (num_tests - done + fpg - 1) // fpg)
         last_frames = min(fpg, num_tests - done - (graphs - 1) * fpg)
-        part = ens(gi, graphs) if last_frames == fpg else ens(gi, graphs - 1) + ens(gi + graphs - 1, 1, last_frames) \
-            if graphs > 1 else ens(gi, 1, last_frames)
+        if last_frames == fpg:
+            part = ens(gi, graphs)
+        else:   # the run ends inside the last graph of this batch
+            part = ens(gi + graphs - 1, 1, last_frames)
+            if graphs > 1:
+                part = part + ens(gi, graphs - 1)
         frames_here = (graphs - 1) * fpg + last_frames
         if exact_stop and int(total[its + 1]) + int(part[its + 1]) >= max_block_errors:
             need = max_block_errors - int(total[its + 1])

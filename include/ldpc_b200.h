@@ -117,12 +117,15 @@ int ldpc_b200_kernel_times(ldpc_b200_graph *g, float *ms, int max);
 /* Ensemble Monte-Carlo (run_simulation, parallel_simulator_expurgated.py:200-256): a fresh random simple
  * (dv,dc)-regular graph per `frames_per_graph` frames.  Graph G (global index first_graph + g) is
  * ldpc_b200_generate_graph(n, dv, dc, graph_seed*1000003 + G, gen_mode); its frames are the global frames
- * [G*F, G*F + frames_per_graph) with F = frames_per_graph rounded up to 128, so a run is reproducible and
- * additive over graph ranges.  counters: HOST [npoints][iterations+6], overwritten.  n < 65536. */
+ * [G*F, G*F + frames_per_graph) with F = frame_stride (a multiple of 128, >= frames_per_graph; 0 = frames_per_graph
+ * rounded up to 128), so a run is reproducible and additive over graph ranges, and a call with fewer frames per
+ * graph and the same frame_stride decodes a PREFIX of every graph's frames (the drivers use that to stop exactly at
+ * the 200th block error, parallel_simulator_expurgated.py:200).  counters: HOST [npoints][iterations+6],
+ * overwritten.  n < 65536. */
 int ldpc_b200_mc_run_ensemble(int device, int n, int dv, int dc, uint64_t graph_seed, int gen_mode,
                               uint64_t first_graph, uint64_t num_graphs, uint32_t frames_per_graph,
-                              const double *eps, int npoints, uint64_t seed, int iterations, int expurgation,
-                              uint64_t *counters, ldpc_b200_mc_stats *stats);
+                              uint32_t frame_stride, const double *eps, int npoints, uint64_t seed, int iterations,
+                              int expurgation, uint64_t *counters, ldpc_b200_mc_stats *stats);
 
 /* Batched decode: Mvc HOST [frames][n] int8 in {0,1,2}, decoded in place; errors HOST
  * [frames][iterations] receives what message_passing.c leaves in a zeroed errors[]; ret [frames]. */
