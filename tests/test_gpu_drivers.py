@@ -126,16 +126,73 @@ def test_mc_run_ensemble_in_kernel_generator(S, oracle, n, dv, dc, fpg, graphs, 
     assert np.array_equal(got, want)
 
 
+def _indexed_reference(oracle, L, n, dv, dc, eps, seed, gseed, total_frames, fpg, its, exp):
+    """Reference frame loop over the graphs of the in-kernel generator: graph G decodes frames [G*F, G*F + fpg),
+    the last graph only as many as are left of `total_frames`."""
+    F = (fpg + 127) // 128 * 128
+    want = np.zeros(its + 6, dtype=np.uint64)
+    g, left = 0, total_frames
+    while left > 0:
+        cnt = min(fpg, left)
+        vl, cl = L.generate_graph_indexed(n, dv, dc, gseed, g)
+        want += oracle.best().mc_run(vl, cl, n, n - n * dv // dc, dv, dc, [eps], seed, g * F, cnt, its, exp, nthreads=4)[0]
+        g += 1
+        left -= cnt
+    return want, g
+
+
 def test_run_simulation_ensemble_expurgated(S, oracle):
     import iib_project_ldpc_codes_b200 as L
     p = {"BEC": 0.40, "expurgation": 0, "num_tests": 1000, "iterations": 40, "n": 240, "dv": 3, "dc": 6,
          "optimal": False, "message_passing": True, "seed": 3}
-    r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4, gen_mode=1)
-    graphs = r["graphs"]
-    assert r["num_tests"] == graphs * 128 and r["num_tests"] >= 1000      # whole graphs, rounded up
-    want = _ensemble_reference(oracle, L, 240, 3, 6, [0.40], 3, 3, 0, graphs, 128, 40, 0)[0]
+    r = S.run_simulation(p, write_csv=False, stop_rule_graphs=4, gen_mode=1, max_block_errors=10 ** 9)
+    assert r["num_tests"] == 1000 and r["graphs"] == 8      # 7 whole graphs + 104 frames of the eighth
+    want = _ensemble_reference(oracle, L, 240, 3, 6, [0.40], 3, 3, 0, 7, 128, 40, 0)[0]
+    vl, cl = L.generate_graph(240, 3, 6, seed=3 * 1000003 + 7, mode=1)
+    want = want + oracle.best().mc_run(vl, cl, 240, 120, 3, 6, [0.40], 3, 7 * 128, 104, 40, 0, nthreads=4)[0]
     assert np.array_equal(r["counters"], want)
     assert "regular_code_expurgated=0_BEC=0.4_n=240" in r["filename"]
+
+
+def test_run_simulation_default_generator_is_the_in_kernel_one(S, oracle):
+    """run_simulation(dict) exactly as parallel_simulator_expurgated.py:418-428 builds the dict, default gen_mode (2):
+    the counters equal the reference frame loop on the host twins of the graphs the kernel generated."""
+    import iib_project_ldpc_codes_b200 as L
+    p = {"BEC": 0.36, "expurgation": 0, "num_tests": 2000, "iterations": 60, "n": 240, "dv": 3, "dc": 6,
+         "optimal": False, "message_passing": True, "seed": 3}
+    r = S.run_simulation(p, write_csv=False)
+    assert r["num_tests"] == 2000
+    want, graphs = _indexed_reference(oracle, L, 240, 3, 6, 0.36, 3, 3, 2000, 128, 60, 0)
+    assert r["graphs"] == graphs and np.array_equal(r["counters"], want)
+    assert r["bp_threshold"] == pytest.approx(0.429440, abs=2e-6) and "scaling_law" in r and "density_evolution" in r
+
+
+def test_cli_mode0_ensemble_with_expurgation(S, oracle):
+    """CLI mode 0 (parallel_simulator_expurgated.py:418-428): eps num_tests iterations n dv dc 0 seed expurgation."""
+    import iib_project_ldpc_codes_b200 as L
+    r = S.main(["prog", "0.36", "2000", "60", "240", "3", "6", "0", "3", "0"])
+    want, graphs = _indexed_reference(oracle, L, 240, 3, 6, 0.36, 3, 3, 2000, 128, 60, 0)
+    assert r["num_tests"] == 2000 and r["graphs"] == graphs and np.array_equal(r["counters"], want)
+    rows = list(csv.reader(open(os.path.join(S.base_directory, "report_data", "simulation_data", r["filename"]))))
+    assert len(rows) == 63 and rows[61][0] == "Message passing block-wise error"
+    # a different expurgation threshold changes what is counted, not the denominators
+    r5 = S.main(["prog", "0.36", "2000", "60", "240", "3", "6", "0", "3", "5"])
+    want5, _ = _indexed_reference(oracle, L, 240, 3, 6, 0.36, 3, 3, 2000, 128, 60, 5)
+    assert np.array_equal(r5["counters"], want5) and r5["num_tests"] == 2000
+
+
+@pytest.mark.parametrize("fpg", [128, 300])
+def test_ensemble_stop_rule_is_exact(S, oracle, fpg):
+    """:200 `while block_error<200`: the run ends with the frame of the 200th counted failure, also inside a graph."""
+    import iib_project_ldpc_codes_b200 as L
+    p = {"BEC": 0.44, "expurgation": 2, "num_tests": 100000, "iterations": 40, "n": 240, "dv": 3, "dc": 6,
+         "optimal": False, "message_passing": True, "seed": 9}
+    r = S.run_simulation(p, write_csv=False, frames_per_graph=fpg, stop_rule_graphs=3)
+    assert r["block_errors"] == 200 and r["num_tests"] < 100000
+    want, graphs = _indexed_reference(oracle, L, 240, 3, 6, 0.44, 9, 9, r["num_tests"], fpg, 40, 2)
+    assert np.array_equal(r["counters"], want) and r["graphs"] == graphs
+    shorter, _ = _indexed_reference(oracle, L, 240, 3, 6, 0.44, 9, 9, r["num_tests"] - 1, fpg, 40, 2)
+    assert int(shorter[41]) == 199      # the last frame of the run is the 200th counted block error
 
 
 def test_cli_modes(S):
