@@ -48,6 +48,94 @@ struct StageParams {
     unsigned long long* stop_hist;        // optional [npoints][cap+1]: frames by executed-iteration count
 };
 
+// Everything after a group's iterations [lo, age): which frames are deferred to the next stage, the residual of the
+// finished ones, the flush of the stage's statistics, and the spill of the deferred frames (bit-packed,
+// frame-major) for the next launch.  Shared by the staged kernel and the overlapped stage-0 kernel (e1_overlap.cuh).
+template <int WORDS>
+__device__ __forceinline__ void stage_finish_group(const E1Params& P, const StageParams& S, const TeamCtx& t, VecT<WORDS>* x,
+                                                   const uint32_t* hbuf, uint32_t* work_slot, uint32_t point, int lo, int hi,
+                                                   int age, const uint32_t (&valid)[WORDS], const uint32_t (&running)[WORDS],
+                                                   const uint32_t (&any)[WORDS], uint32_t cnt, unsigned long long exec_sum) {
+    constexpr int W = 32 * WORDS;
+    unsigned long long* C = P.counters + (size_t)point * raw_stride(P.cap);
+    // frames still running at a stage boundary below the cap are deferred to the next stage
+    uint32_t D[WORDS], F[WORDS], ndef = 0;
+    LDPC_FORW {
+        D[w] = (age == hi && hi < P.cap) ? running[w] : 0u;
+        F[w] = valid[w] & ~D[w];
+        ndef += __popc(D[w]);
+    }
+    if (S.stop_hist && t.tid == 0 && hi >= P.cap) {
+        uint32_t capped = 0;
+        LDPC_FORW capped += __popc(running[w]);
+        red_add(S.stop_hist + (size_t)point * (P.cap + 1) + P.cap, capped);   // ran every iteration up to the cap
+    }
+    uint32_t resid = cnt;   // erased count of the finished frames
+    if (ndef) {
+        uint32_t none[1] = {0u};
+        resid = 0;
+        for (int i = t.tid; i < P.n; i += t.nthr) {
+            const VecT<WORDS> xi = x[i];
+            LDPC_FORW resid += __popc(xi.a[w] & F[w]);
+        }
+        team_reduce<1>(t, none, resid);
+    }
+    // ---- flush the statistics of this stage
+    team_sync(t);
+    const int first_bin = S.stage == 0 ? 0 : 1;
+    for (int b = first_bin + t.tid; b <= age - lo; b += t.nthr) red_add(C + lo + b, hbuf[b]);
+    if (t.tid == 0) {
+        if (age < P.cap) red_add(C + P.cap + 6 + age + 1, resid);   // bins after `age` keep the finished frames' residual
+        uint32_t blk = 0, nv = 0;
+        LDPC_FORW { blk += __popc(any[w] & F[w]); nv += __popc(valid[w]); }
+        red_add(C + P.cap + 1, blk);
+        red_add(C + P.cap + 2, resid);
+        if (S.stage == 0) { red_add(C + P.cap + 3, nv); red_add(C + P.cap + 4, nv); }
+        red_add(C + P.cap + 5, exec_sum);
+        red_add(C + 2 * P.cap + 8, (unsigned long long)(age - lo) * W);
+    }
+    // ---- spill the deferred frames (bit-packed, frame-major) for the next stage
+    if (ndef) {
+        unsigned long long sbase;
+        if (t.team_warps == 1) {
+            unsigned long long v = 0;
+            if (t.lane == 0) v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+            sbase = __shfl_sync(0xFFFFFFFFu, v, 0);
+        } else {
+            if (t.tid == 0) {
+                unsigned long long v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+                work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+            }
+            team_sync(t);
+            sbase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+        }
+        uint32_t* out = S.spill_out + (size_t)point * S.point_stride * S.rec_words;
+        for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
+            uint32_t before = 0;
+            const int s0 = 32 * j0 + t.lane;
+            VecT<WORDS> v[4];   // whole-vector loads of variables s0, s0+32, s0+64, s0+96 (no bank conflicts)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (s0 + 32 * k < P.n) v[k] = x[s0 + 32 * k];
+                else { LDPC_FORW v[k].a[w] = 0u; }
+            }
+            LDPC_FORW {
+                if (D[w] == 0u) continue;   // team-uniform: no survivor in this word, nothing to transpose
+                uint4 r;
+                r.x = transpose32(v[0].a[w], t.lane);
+                r.y = transpose32(v[1].a[w], t.lane);
+                r.z = transpose32(v[2].a[w], t.lane);
+                r.w = transpose32(v[3].a[w], t.lane);
+                if ((D[w] >> t.lane) & 1u) {
+                    const unsigned long long rec = sbase + before + __popc(D[w] & ((1u << t.lane) - 1u));
+                    *reinterpret_cast<uint4*>(out + (size_t)rec * S.rec_words + j0) = r;
+                }
+                before += __popc(D[w]);
+            }
+        }
+    }
+}
+
 template <int WORDS, int DV, int DC, bool TM = false>
 __global__ void __launch_bounds__(e1_threads(WORDS), 1)
 e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
@@ -212,82 +300,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             }
             if (S.stop_hist && t.tid == 0) red_add(S.stop_hist + (size_t)point * (P.cap + 1) + age + 1, stopped);
         }
-        // frames still running at a stage boundary below the cap are deferred to the next stage
-        uint32_t D[WORDS], F[WORDS], ndef = 0;
-        LDPC_FORW {
-            D[w] = (age == hi && hi < P.cap) ? running[w] : 0u;
-            F[w] = valid[w] & ~D[w];
-            ndef += __popc(D[w]);
-        }
-        if (S.stop_hist && t.tid == 0 && hi >= P.cap) {
-            uint32_t capped = 0;
-            LDPC_FORW capped += __popc(running[w]);
-            red_add(S.stop_hist + (size_t)point * (P.cap + 1) + P.cap, capped);   // ran every iteration up to the cap
-        }
-        uint32_t resid = cnt;   // erased count of the finished frames
-        if (ndef) {
-            uint32_t none[1] = {0u};
-            resid = 0;
-            for (int i = t.tid; i < P.n; i += t.nthr) {
-                const VecT<WORDS> xi = x[i];
-                LDPC_FORW resid += __popc(xi.a[w] & F[w]);
-            }
-            team_reduce<1>(t, none, resid);
-        }
-        // ---- flush the statistics of this stage
-        team_sync(t);
-        const int first_bin = S.stage == 0 ? 0 : 1;
-        for (int b = first_bin + t.tid; b <= age - lo; b += t.nthr) red_add(C + lo + b, hbuf[b]);
-        if (t.tid == 0) {
-            if (age < P.cap) red_add(C + P.cap + 6 + age + 1, resid);   // bins after `age` keep the finished frames' residual
-            uint32_t blk = 0, nv = 0;
-            LDPC_FORW { blk += __popc(any[w] & F[w]); nv += __popc(valid[w]); }
-            red_add(C + P.cap + 1, blk);
-            red_add(C + P.cap + 2, resid);
-            if (S.stage == 0) { red_add(C + P.cap + 3, nv); red_add(C + P.cap + 4, nv); }
-            red_add(C + P.cap + 5, exec_sum);
-            red_add(C + 2 * P.cap + 8, (unsigned long long)(age - lo) * W);
-        }
-        // ---- spill the deferred frames (bit-packed, frame-major) for the next stage
-        if (ndef) {
-            unsigned long long sbase;
-            if (t.team_warps == 1) {
-                unsigned long long v = 0;
-                if (t.lane == 0) v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
-                sbase = __shfl_sync(0xFFFFFFFFu, v, 0);
-            } else {
-                if (t.tid == 0) {
-                    unsigned long long v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
-                    work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
-                }
-                team_sync(t);
-                sbase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
-            }
-            uint32_t* out = S.spill_out + (size_t)point * S.point_stride * S.rec_words;
-            for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
-                uint32_t before = 0;
-                const int s0 = 32 * j0 + t.lane;
-                VecT<WORDS> v[4];   // whole-vector loads of variables s0, s0+32, s0+64, s0+96 (no bank conflicts)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (s0 + 32 * k < P.n) v[k] = x[s0 + 32 * k];
-                    else { LDPC_FORW v[k].a[w] = 0u; }
-                }
-                LDPC_FORW {
-                    if (D[w] == 0u) continue;   // team-uniform: no survivor in this word, nothing to transpose
-                    uint4 r;
-                    r.x = transpose32(v[0].a[w], t.lane);
-                    r.y = transpose32(v[1].a[w], t.lane);
-                    r.z = transpose32(v[2].a[w], t.lane);
-                    r.w = transpose32(v[3].a[w], t.lane);
-                    if ((D[w] >> t.lane) & 1u) {
-                        const unsigned long long rec = sbase + before + __popc(D[w] & ((1u << t.lane) - 1u));
-                        *reinterpret_cast<uint4*>(out + (size_t)rec * S.rec_words + j0) = r;
-                    }
-                    before += __popc(D[w]);
-                }
-            }
-        }
+        stage_finish_group<WORDS>(P, S, t, x, hbuf, work_slot, point, lo, hi, age, valid, running, any, cnt, exec_sum);
         team_sync(t);   // shared state is rewritten by the next group
     }
     if constexpr (TM) tm_free_all(tm_base);

@@ -130,7 +130,7 @@ static int tuning_env(const char* name) {
 static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg) {
     if (!((g->dv == 3 && g->dc == 6) || (g->dv == 4 && g->dc == 8))) return false;   // degree pairs the kernels are specialised for
     if (g->n > 65535 || tuning_env("LDPC_B200_TMEM") == 2) return false;
-    const uint32_t limit = (uint32_t)g->smem_optin;
+    const uint32_t limit = (uint32_t)g->smem_optin - 64;   // the kernels' static shared memory (the TMEM base slot)
     const int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
     const int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
     const int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
