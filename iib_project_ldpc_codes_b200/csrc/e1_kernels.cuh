@@ -120,6 +120,12 @@ struct E1Params {
     unsigned long long groups_per_point;
     unsigned long long* counters;       // [npoints][raw_stride(cap)]
     unsigned long long* work_counter;
+    // expurgation re-count (pass 2 of the two-pass expurgated run, e1_staged.cuh): the work items are groups of the
+    // frames the staged pass listed (chunk-relative frame ids); denominators are NOT added again
+    int recount;
+    const uint32_t* rc_ids;              // [npoints][rc_stride]
+    const unsigned long long* rc_cnt;    // [npoints]
+    unsigned long long rc_stride;
     // batched decode work (WORDS == 1)
     const uint32_t* xin;   // [groups][n] erasure plane
     const uint32_t* vin;   // [groups][n] value plane
@@ -692,6 +698,41 @@ __device__ __forceinline__ void stage_v2c_resident(const E1Params& P, unsigned c
     }
 }
 
+// team scratch, in 32-bit words: reduce area | work slot | per-frame counts (rf) | draw queue counters | frame ids
+__host__ __device__ constexpr int e1_scr_words(int words) { return 32 * (2 * words + 1) + 2 + 32 * words + 8 + 32 * words; }
+
+// Channel draw for a group of ARBITRARY frames (one chunk-relative frame id per lane in fid[]): a warp takes one
+// variable at a time, lane l decides frame l's bit alone (bec_lane_bit) and a ballot assembles the bit-sliced word.
+template <int WORDS, bool MASKED>
+__device__ __forceinline__ void team_draw_lanes(const E1Params& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
+                                                const uint32_t* fid, const uint32_t (&valid)[WORDS],
+                                                const uint32_t (&mask)[WORDS], VecT<WORDS>* x, uint32_t (&red)[WORDS],
+                                                uint32_t& cnt) {
+    LDPC_FORW red[w] = 0u;
+    cnt = 0u;
+    BecParams bp = bp_;
+    bp.seed_lo = P.seed_lo; bp.seed_hi = P.seed_hi;
+    unsigned long long q[WORDS];
+    uint32_t bit[WORDS];
+    LDPC_FORW {
+        const unsigned long long f = P.first_word * 32ull + (unsigned long long)fid[w * 32 + t.lane];
+        q[w] = f >> 5; bit[w] = (uint32_t)f & 31u;
+    }
+    for (int i = t.warp; i < P.n; i += t.team_warps) {
+        const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
+        VecT<WORDS> xi;
+        LDPC_FORW {
+            const bool on = (valid[w] >> t.lane) & 1u;
+            const uint32_t b = on ? bec_lane_bit(bp, point, q[w], var, bit[w]) : 0u;
+            xi.a[w] = __ballot_sync(0xFFFFFFFFu, b != 0u);
+        }
+        if (t.lane == 0) {
+            x[i] = xi;
+            LDPC_FORW { red[w] |= xi.a[w]; cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]); }
+        }
+    }
+}
+
 // Decode one frame group for the Monte-Carlo path.  MASKED pass: erasure sums restricted to `mask`.
 // Returns physical iterations executed; outputs the team-uniform masks / counts by reference.
 template <int WORDS, int DV, int DC, bool MASKED, bool TM = false>
@@ -702,8 +743,11 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
                                         uint32_t& cnt, unsigned long long& exec_sum) {
     // draw the erasure pattern (channels.py:24-26) straight into shared memory
     uint32_t red[WORDS];
-    team_draw<WORDS, MASKED>(P, t, bp, point, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
-                             t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
+    if (P.recount)
+        team_draw_lanes<WORDS, MASKED>(P, t, bp, point, t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS + 8, valid, mask, x, red, cnt);
+    else
+        team_draw<WORDS, MASKED>(P, t, bp, point, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
+                                 t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
     team_reduce<WORDS>(t, red, cnt);
     LDPC_FORW any[w] = red[w];
     if (t.tid == 0) hbuf[0] = cnt;
@@ -784,9 +828,14 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         tm_fill_lists<WORDS, DV, DC>(P, t, tm_base);
     }
 
-    const unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
+    unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
     const int W = 32 * WORDS;
     const int stride = raw_stride(P.cap);
+    uint32_t* fid = rf + 32 * WORDS + 8;   // recount: chunk-relative ids of the group's frames
+    if (P.recount) {
+        total = 0;
+        for (int p = 0; p < P.npoints; p++) total += (P.rc_cnt[p] + W - 1) / W;
+    }
     if (P.ens) {
         s_c2v = reinterpret_cast<uint16_t*>(base + P.sm_c2v);
         s_v2c = reinterpret_cast<uint16_t*>(base + P.sm_v2c);
@@ -809,13 +858,32 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
             item = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
         }
         if (item >= total) break;
-        const uint32_t point = (uint32_t)(item / P.groups_per_point);
-        const unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
+        uint32_t point = (uint32_t)(item / P.groups_per_point);
+        unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
+        uint32_t valid[WORDS];
+        if (P.recount) {   // group gi of the listed frames of `point`
+            unsigned long long rest = item;
+            int p = 0;
+            for (; p < P.npoints; p++) {
+                const unsigned long long gp = (P.rc_cnt[p] + W - 1) / W;
+                if (rest < gp) break;
+                rest -= gp;
+            }
+            point = (uint32_t)p; gi = rest;
+            const unsigned long long left = P.rc_cnt[p] - gi * W;
+            LDPC_FORW {
+                const unsigned long long f0 = (unsigned long long)w * 32ull;
+                valid[w] = f0 >= left ? 0u : (left - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(left - f0)) - 1u));
+            }
+            for (int f = t.tid; f < W; f += t.nthr)
+                fid[f] = (unsigned long long)f < left ? P.rc_ids[(size_t)p * P.rc_stride + gi * W + f] : 0u;
+            team_sync(t);
+        }
         unsigned long long q0 = P.first_word + gi * WORDS;
         const BecParams bp = P.bec[point];
 
-        uint32_t valid[WORDS];
-        if (!P.ens) {
+        if (P.recount) {
+        } else if (!P.ens) {
             LDPC_FORW {
                 const unsigned long long f0 = (gi * WORDS + w) * 32ull;  // first frame of this word, relative
                 valid[w] = f0 >= P.num_frames ? 0u
@@ -884,8 +952,7 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
             if (kany == 0u) {
                 // nothing counted: only the denominators move
                 if (t.tid == 0) {
-                    red_add(C + P.cap + 3, nvalid);
-                    red_add(C + P.cap + 5, exec_sum);
+                    if (!P.recount) { red_add(C + P.cap + 3, nvalid); red_add(C + P.cap + 5, exec_sum); }
                     red_add(C + 2 * P.cap + 8, phys);
                 }
                 continue;
@@ -908,9 +975,9 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
             LDPC_FORW { blk += __popc(any[w] & K[w]); nk += __popc(K[w]); }
             red_add(C + P.cap + 1, blk);
             red_add(C + P.cap + 2, cnt);
-            red_add(C + P.cap + 3, nvalid);
+            if (!P.recount) red_add(C + P.cap + 3, nvalid);   // the listing pass counted the denominators
             red_add(C + P.cap + 4, nk);
-            red_add(C + P.cap + 5, exec_sum);
+            if (!P.recount) red_add(C + P.cap + 5, exec_sum);
             red_add(C + 2 * P.cap + 8, phys);
             if (second) red_add(C + 2 * P.cap + 9, 1ull);
         }

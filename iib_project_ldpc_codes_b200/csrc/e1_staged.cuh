@@ -46,6 +46,14 @@ struct StageParams {
     unsigned long long point_stride;      // record capacity per point
     int rec_words;                        // 32-bit words per record = ceil(n/32) rounded up to 4
     unsigned long long* stop_hist;        // optional [npoints][cap+1]: frames by executed-iteration count
+    // Expurgated run (parallel_simulator_expurgated.py:238: only frames whose final residual exceeds the threshold
+    // contribute to any statistic), pass 1: the staged pipeline adds the denominators only (frames, executed
+    // iterations) and LISTS every frame that ends with erasures left; pass 2 (e1_mc_kernel, recount) re-draws exactly
+    // those frames, packs them into dense groups and accumulates their statistics.  Every spill record carries its
+    // frame's chunk-relative id in its last word (rec_words >= ceil(n/32) + 1).
+    int exp_mode;
+    uint32_t* id_list;                    // [npoints][point_stride]
+    unsigned long long* id_cnt;           // [npoints] (atomic)
 };
 
 // Everything after a group's iterations [lo, age): which frames are deferred to the next stage, the residual of the
@@ -55,7 +63,8 @@ template <int WORDS>
 __device__ __forceinline__ void stage_finish_group(const E1Params& P, const StageParams& S, const TeamCtx& t, VecT<WORDS>* x,
                                                    const uint32_t* hbuf, uint32_t* work_slot, uint32_t point, int lo, int hi,
                                                    int age, const uint32_t (&valid)[WORDS], const uint32_t (&running)[WORDS],
-                                                   const uint32_t (&any)[WORDS], uint32_t cnt, unsigned long long exec_sum) {
+                                                   const uint32_t (&any)[WORDS], uint32_t cnt, unsigned long long exec_sum,
+                                                   const uint32_t* fid /* shared: chunk-relative frame id per lane */) {
     constexpr int W = 32 * WORDS;
     unsigned long long* C = P.counters + (size_t)point * raw_stride(P.cap);
     // frames still running at a stage boundary below the cap are deferred to the next stage
@@ -71,7 +80,7 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
         red_add(S.stop_hist + (size_t)point * (P.cap + 1) + P.cap, capped);   // ran every iteration up to the cap
     }
     uint32_t resid = cnt;   // erased count of the finished frames
-    if (ndef) {
+    if (ndef && !S.exp_mode) {
         uint32_t none[1] = {0u};
         resid = 0;
         for (int i = t.tid; i < P.n; i += t.nthr) {
@@ -83,16 +92,42 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
     // ---- flush the statistics of this stage
     team_sync(t);
     const int first_bin = S.stage == 0 ? 0 : 1;
-    for (int b = first_bin + t.tid; b <= age - lo; b += t.nthr) red_add(C + lo + b, hbuf[b]);
+    if (!S.exp_mode)
+        for (int b = first_bin + t.tid; b <= age - lo; b += t.nthr) red_add(C + lo + b, hbuf[b]);
     if (t.tid == 0) {
-        if (age < P.cap) red_add(C + P.cap + 6 + age + 1, resid);   // bins after `age` keep the finished frames' residual
         uint32_t blk = 0, nv = 0;
         LDPC_FORW { blk += __popc(any[w] & F[w]); nv += __popc(valid[w]); }
-        red_add(C + P.cap + 1, blk);
-        red_add(C + P.cap + 2, resid);
-        if (S.stage == 0) { red_add(C + P.cap + 3, nv); red_add(C + P.cap + 4, nv); }
+        if (!S.exp_mode) {
+            if (age < P.cap) red_add(C + P.cap + 6 + age + 1, resid);   // bins after `age` keep the finished frames' residual
+            red_add(C + P.cap + 1, blk);
+            red_add(C + P.cap + 2, resid);
+            if (S.stage == 0) red_add(C + P.cap + 4, nv);
+        }
+        if (S.stage == 0) red_add(C + P.cap + 3, nv);
         red_add(C + P.cap + 5, exec_sum);
         red_add(C + 2 * P.cap + 8, (unsigned long long)(age - lo) * W);
+    }
+    // ---- expurgated run: list the finished frames that still have erasures (they are re-drawn and counted in pass 2)
+    if (S.exp_mode) {
+        uint32_t E[WORDS], nemit = 0;
+        LDPC_FORW { E[w] = any[w] & F[w]; nemit += __popc(E[w]); }
+        if (nemit) {   // team-uniform
+            if (t.tid == 0) {
+                const unsigned long long v = atomicAdd(S.id_cnt + point, (unsigned long long)nemit);
+                work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+            }
+            team_sync(t);
+            const unsigned long long ebase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+            team_sync(t);   // work_slot is reused for the spill base below
+            if (t.warp == 0) {
+                uint32_t before = 0;
+                LDPC_FORW {
+                    if ((E[w] >> t.lane) & 1u)
+                        S.id_list[(size_t)point * S.point_stride + ebase + before + __popc(E[w] & ((1u << t.lane) - 1u))] = fid[w * 32 + t.lane];
+                    before += __popc(E[w]);
+                }
+            }
+        }
     }
     // ---- spill the deferred frames (bit-packed, frame-major) for the next stage
     if (ndef) {
@@ -126,6 +161,7 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
                 r.y = transpose32(v[1].a[w], t.lane);
                 r.z = transpose32(v[2].a[w], t.lane);
                 r.w = transpose32(v[3].a[w], t.lane);
+                if (S.exp_mode && j0 + 4 == S.rec_words) r.w = fid[w * 32 + t.lane];   // the record's last word: its frame id
                 if ((D[w] >> t.lane) & 1u) {
                     const unsigned long long rec = sbase + before + __popc(D[w] & ((1u << t.lane) - 1u));
                     *reinterpret_cast<uint4*>(out + (size_t)rec * S.rec_words + j0) = r;
@@ -172,6 +208,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
     uint32_t* hbuf = reinterpret_cast<uint32_t*>(base + P.sm_hbuf);
     t.scr = reinterpret_cast<uint32_t*>(base + P.sm_scr);
     uint32_t* work_slot = t.scr + 32 * (2 * WORDS + 1);
+    uint32_t* fid = work_slot + 2 + 32 * WORDS + 8;   // chunk-relative frame id per lane (expurgated runs)
     uint32_t tm_base = 0;
     if constexpr (TM) {   // socket lists -> tensor memory (e1_tmem.cuh)
         tm_base = tm_alloc_all(&tm_slot);
@@ -241,11 +278,16 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             uint32_t red[WORDS];
             team_draw<WORDS, false>(P, t, bp, point, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
                                     t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
+            if (S.exp_mode)
+                for (int f = t.tid; f < W; f += t.nthr) fid[f] = (uint32_t)(gi * W + f);
             team_reduce<WORDS>(t, red, cnt);
             LDPC_FORW any[w] = red[w];
             if (t.tid == 0) hbuf[0] = cnt;
         } else {
             const uint32_t* recs = S.spill_in + ((size_t)point * S.point_stride + gi * W) * S.rec_words;
+            if (S.exp_mode)
+                for (int f = t.tid; f < W; f += t.nthr)
+                    fid[f] = (unsigned long long)f < S.cnt_in[point] - gi * W ? recs[(size_t)f * S.rec_words + S.rec_words - 1] : 0u;
             for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
                 VecT<WORDS> o[4];   // state vectors of variables s0, s0+32, s0+64, s0+96: whole-vector stores (no bank conflicts)
                 LDPC_FORW {
@@ -300,7 +342,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             }
             if (S.stop_hist && t.tid == 0) red_add(S.stop_hist + (size_t)point * (P.cap + 1) + age + 1, stopped);
         }
-        stage_finish_group<WORDS>(P, S, t, x, hbuf, work_slot, point, lo, hi, age, valid, running, any, cnt, exec_sum);
+        stage_finish_group<WORDS>(P, S, t, x, hbuf, work_slot, point, lo, hi, age, valid, running, any, cnt, exec_sum, fid);
         team_sync(t);   // shared state is rewritten by the next group
     }
     if constexpr (TM) tm_free_all(tm_base);

@@ -69,6 +69,7 @@ struct StagePlan {
     std::vector<int> cuts;   // [npoints][nstages+1]
     double predicted_inflation = 0;
     unsigned long long pilot_frames = 0;   // frames per point the pilot decoded (a much larger run draws a better one)
+    double pilot_fer = 0;                  // largest block error rate over the points, as the pilot saw it
 };
 
 struct ldpc_b200_graph {
@@ -96,6 +97,7 @@ struct ldpc_b200_graph {
     // staged E1 Monte-Carlo: cut points per (eps list, cap, words), spill buffers, per-stage record counts
     std::unordered_map<uint64_t, StagePlan> plans;
     void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0;
+    uint32_t* d_idlist = nullptr; size_t idlist_bytes = 0;   // expurgated runs: frames listed for the re-count pass
     unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
     int* d_cuts = nullptr; size_t cuts_cap = 0;
     // batched decode buffers (cached between calls)
@@ -144,7 +146,7 @@ static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg) {
         c.sm_t = off; off += align_up((uint32_t)g->m * 4 * words, 16);
         c.sm_v = off; c.sm_p = off;
         c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
-        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words + 8) * 4, 16);
+        c.sm_scr = off; off += align_up((uint32_t)e1_scr_words(words) * 4, 16);
         const uint32_t tb = off;
         if (tb > limit) continue;
         const int max_warps = e1_threads(words) / 32;
@@ -187,7 +189,7 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
         c.sm_v = off; if (values) off += align_up((uint32_t)g->n * 4 * words, 16);
         c.sm_p = off; if (values) off += align_up((uint32_t)g->m * 4 * words, 16);
         c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
-        c.sm_scr = off; off += align_up((uint32_t)(32 * (2 * words + 1) + 2 + 32 * words + 8) * 4, 16);
+        c.sm_scr = off; off += align_up((uint32_t)e1_scr_words(words) * 4, 16);
         return off;
     };
     int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
@@ -327,7 +329,7 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
     cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
     cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
-    cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_cuts);
+    cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_cuts); cudaFree(g->d_idlist);
     cudaFree(g->dec_mvc); cudaFree(g->dec_x); cudaFree(g->dec_v); cudaFree(g->dec_err); cudaFree(g->dec_ret);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
@@ -587,11 +589,17 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     if (rc) return rc;
     // staged path: survivors are re-packed between stages (e1_staged.cuh); exact, used when every frame
     // counts (no expurgation mask) and the run is long enough to amortise the pilot
+    // Expurgated runs (expurgation >= 0) take the same pipeline as a listing pass + a re-count of the listed frames
+    // (e1_staged.cuh) unless the pilot saw a block error rate at which re-drawing the failed frames one by one
+    // would cost more than decoding mixed groups twice (the unstaged kernel below).
     StagePlan* plan = nullptr;
-    if (expurgation < 0 && num_frames >= 8192 && tuning_env("LDPC_B200_STAGES") != 1) {
+    bool two_pass = false;
+    if (num_frames >= 8192 && tuning_env("LDPC_B200_STAGES") != 1 && (expurgation < 0 || tuning_env("LDPC_B200_EXP2PASS") != 2)) {
         rc = get_stage_plan(g, cfg, P, eps, npoints, seed, cap, num_frames, st, &plan);
         if (rc) return rc;
-        if (plan->nstages <= 1) plan = nullptr;
+        two_pass = expurgation >= 0 && (plan->pilot_fer <= 0.10 || tuning_env("LDPC_B200_EXP2PASS") == 1);
+        if (expurgation >= 0 && !two_pass) plan = nullptr;
+        else if (plan->nstages <= 1 && !two_pass) plan = nullptr;
         // the pilot (first call per plan key) pulls its groups from the same work counter: start from zero again
         CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
     }
@@ -599,7 +607,7 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));
     int grid_used = grid;
     if (plan) {
-        rc = e1_mc_staged(g, cfg, P, *plan, npoints, first_frame, num_frames, st, &grid_used);
+        rc = e1_mc_staged(g, cfg, P, *plan, npoints, first_frame, num_frames, two_pass, expurgation, st, &grid_used);
         if (rc) return rc;
         g->last_stages = plan->nstages;
     } else {

@@ -129,3 +129,51 @@ def test_small_runs_use_a_small_pilot_and_stay_exact(L, oracle, frames):
     got2 = g.mc_run(eps, seed + 1, big, its)
     want2 = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed + 1, 0, big, its, -1, nthreads=16)
     assert np.array_equal(got2, want2)
+
+
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("words,expurgation", [(4, 0), (4, 5), (2, 0), (2, 40), (1, 3)])
+def test_expurgated_two_pass_equals_reference(L, oracle, words, expurgation):
+    """parallel_simulator_expurgated.py:238-243 at run sizes that take the staged pipeline: pass 1 lists the frames that end
+    with erasures (ids travel in the spill records), pass 2 re-draws and counts exactly those.  Forced on for every
+    point (eps = 0.43 fails often) and with forced cuts so that listed frames come out of every stage."""
+    vl, cl = L.generate_graph(1000, 3, 6, seed=1, mode=1)
+    eps, seed, frames, its = [0.36, 0.40, 0.43], 99, 20000 + 33, 200
+    want = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed, 128, frames, its, expurgation, nthreads=16)
+    for env in ({"LDPC_B200_EXP2PASS": 1}, {"LDPC_B200_EXP2PASS": 1, "LDPC_B200_FORCE_CUTS": "6,11,19,40"},
+                {"LDPC_B200_EXP2PASS": 2}):
+        g = L.Graph(vl, cl)
+        g.set_tuning(words, 0, 0)
+        got, st = _with_env(env, lambda: g.mc_run(eps, seed, frames, its, expurgation=expurgation, first_frame=128,
+                                                  return_stats=True))
+        assert np.array_equal(got, want), f"{env} words={words}"
+        if env["LDPC_B200_EXP2PASS"] == 1:
+            assert st["stages"] >= (5 if "LDPC_B200_FORCE_CUTS" in env else 1) and st["second_pass_groups"] == (0 if expurgation == 0 else st["second_pass_groups"])
+        g.close()
+
+
+def test_expurgated_two_pass_other_code_and_chunks(L, oracle):
+    """(4,8) n=2000 (BASELINE config 4's code), several chunks (small spill budget), automatic choice of the strategy."""
+    vl, cl = L.generate_graph(2000, 4, 8, seed=4, mode=1)
+    eps, seed, frames, its = [0.31, 0.35], 5, 30000, 200
+    want = oracle.best().mc_run(vl, cl, 2000, 1000, 4, 8, eps, seed, 0, frames, its, 0, nthreads=16)
+    g = L.Graph(vl, cl)
+    got, st = _with_env({"LDPC_B200_SPILL_MB": 2}, lambda: g.mc_run(eps, seed, frames, its, expurgation=0, return_stats=True))
+    assert np.array_equal(got, want)
+    assert st["kernel_launches"] > 10      # listing stages + one re-count launch per chunk
+    # above the threshold nearly every frame fails: the strategy switches to the masked second pass, same counters
+    hi = oracle.best().mc_run(vl, cl, 2000, 1000, 4, 8, [0.40], seed, 0, 9000, its, 0, nthreads=16)
+    got_hi, st_hi = g.mc_run([0.40], seed, 9000, its, expurgation=0, return_stats=True)
+    assert np.array_equal(got_hi, hi) and st_hi["stages"] == 1
