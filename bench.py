@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the BEC message-passing Monte-Carlo hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c4|c5] [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c4e|c5] [--scaling weak|strong]
+                    [--impl ours|reference] [--no-legs] [--no-cpu-baseline]
 
-One "step" = one pass of the fused Monte-Carlo path over one batch of synthetic input: every erasure
-point of the workload, `frames` frames per point PER GPU (weak scaling: rank r decodes the global frame
-range [r*frames, (r+1)*frames) of every point; the only exchange is one all-reduce of the counter block).
+One "step" = one pass of the fused Monte-Carlo path over one batch of synthetic input: every erasure point of the
+workload, `frames` frames per point.  --scaling weak (default): every GPU decodes `frames` frames per point (rank r
+takes the global frame range [r*frames, (r+1)*frames)); --scaling strong: the `frames` frames per point are split
+over the GPUs (128-aligned slices) and the N-GPU counter block must equal the 1-GPU block bit for bit (asserted).
+The only exchange is one all-reduce of the integer counter block.
 
-Default workload = BASELINE.json configs[1]: (3,6)-regular n=10^4, eps in {0.38..0.43}, 10^7 frames per
-point, iteration cap 200.  Prints ONE JSON line (rank 0).
+Default workload = BASELINE.json configs[1]: (3,6)-regular n=10^4, eps in {0.38..0.43}, 10^7 frames per point,
+iteration cap 200.  Prints ONE JSON line (rank 0).  At N=1 the line also carries two extra legs measured the same
+way (value, e2e, roofline, clocks): "c1" -- the n=1000 eps=0.40 configuration north_star's 10^9 frames/s target is
+quoted on -- and "c3" -- n=10^6, graph streamed from HBM (engine E2).
 """
 from __future__ import annotations
 
@@ -44,12 +49,19 @@ WORKLOADS = {
 }
 GRAPH_SEED = 1
 RUN_SEED = 12345
+SMEM_NOMINAL_B_PER_CLK_SM = 128.0
 
 
-def alg_bytes_per_edge_update(dv, dc, n, words=4):
+def alg_bytes_per_edge_update(dv, dc, n):
     """state bits (2E + m + 2n per frame-iteration) + index bytes amortised over W=128 frames."""
     idx = 2 if n < 65536 else 4
     return (2 + 1 / dc + 2 / dv) / 8 + 2 * idx / 128
+
+
+def config_of(name, wl, scaling):
+    """The SAME dict in both arms (the driver compares it)."""
+    return {"workload": name + ": " + wl["desc"], "frames_per_point": wl["frames"], "iteration_cap": wl["cap"],
+            "expurgation": wl["expurgation"], "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED, "scaling": scaling}
 
 
 class ClockSampler:
@@ -66,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -99,43 +111,84 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own implementation of the path on the box's host cores (oracle/ is test infrastructure;
+# this file's cpu_baseline / --impl reference legs are the places allowed to execute it)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_frames(wl, cores):
+    """bounded sample: ~64 frames per thread and point at n = 10^4 scale (10-20 s of CPU work)"""
+    return max(cores * max(1, int(64 * 10000 / wl["n"])), 1 if wl["n"] > 100000 else 32)
+
+
+def cpu_baseline(wl, vl, cl, fpp=None, with_variants=True, got_fn=None):
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
+    m = n * dv // dc
+    fpp = fpp or cpu_sample_frames(wl, cores)
+    chk = O.best()
+    c, dsec = chk.mc_run(vl, cl, n, n - m, dv, dc, eps, RUN_SEED, 0, fpp, cap, wl["expurgation"], nthreads=cores,
+                         return_seconds=True)
+    frames = int(c[:, cap + 3].sum())
+    out = {"value": frames / dsec, "unit": "frames/s", "cores": cores, "kind": "reference" if O.have_ref() else "port",
+           "sample": f"{fpp} frames/point x {len(eps)} points, unmodified message_passing.c (gcc -O2) in a C frame loop, "
+                     f"decode calls only, {cores} threads",
+           "edge_updates_per_s": int(c[:, cap + 5].sum()) * n * dv / dsec}
+    if got_fn is not None:   # the sample is also a live parity check of the GPU path on the same frames
+        out["parity_on_sample"] = bool(np.array_equal(got_fn(fpp), c))
+    if with_variants:
+        if O.have_ref_o3():   # SURVEY 8(d): the same source at -O3 with AVX2/FMA/BMI (stand-in for -march=native)
+            c3, d3 = O.reference_o3().mc_run(vl, cl, n, n - m, dv, dc, eps, RUN_SEED, 0, fpp, cap, wl["expurgation"],
+                                             nthreads=cores, return_seconds=True)
+            out["O3_x86_64_v3"] = {"value": int(c3[:, cap + 3].sum()) / d3, "unit": "frames/s", "cores": cores,
+                                   "identical_counters": bool(np.array_equal(c3, c))}
+        if O.have_ref() and n <= 100000:
+            # SURVEY 8(d) row (ii): the reference's Python frame loop as shipped (parallel_simulator_expurgated.py:367-392
+            # + :131-167 restated around the unmodified .so), one process on one core, ~4 s
+            from oracle import as_shipped as A
+            fr, sec, _ = A.run_fixed_loop(n, dv, dc, eps[len(eps) // 2], cap, cl, vl, seconds=4.0)
+            out["as_shipped_python_loop"] = {"value": fr / sec, "unit": "frames/s", "cores": 1,
+                                             "sample": f"{fr} frames at eps={eps[len(eps) // 2]} in {sec:.1f} s, numpy channel "
+                                                       "+ ctypes marshalling + CDLL per frame as the reference does"}
+    return out
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = the unmodified
-    message_passing.c compiled here; falls back to the pinned C restatement) on all host threads, on a
-    bounded sample of the same workload."""
+    message_passing.c compiled here; falls back to the pinned C restatement) on all host threads, on a bounded sample
+    of the same workload.  Nothing of the product package or library is loaded: the graph comes from the oracle's own
+    twin of the seeded generator (oracle/graph_twin.h)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
-    import iib_project_ldpc_codes_b200 as L
     O.build()
     kind = "reference" if O.have_ref() else "port"
     chk = O.best()
     cores = os.cpu_count() or 1
-    vl, cl = L.generate_graph(wl["n"], wl["dv"], wl["dc"], seed=GRAPH_SEED, mode=1)
-    m = wl["n"] * wl["dv"] // wl["dc"]
-    # bounded sample: ~64 frames per thread per point at n=10^4 scale
-    fpp = args.ref_frames or max(cores * max(1, int(64 * 10000 / wl["n"])), 1 if wl["n"] > 100000 else 32)
-    eps = wl["eps"]
+    n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
+    vl, cl = O.generate_graph(n, dv, dc, seed=GRAPH_SEED)
+    m = n * dv // dc
+    fpp = args.ref_frames or cpu_sample_frames(wl, cores)
     secs, frames, execs = [], 0, 0
     for s in range(args.warmup + args.steps):
-        c, dsec = chk.mc_run(vl, cl, wl["n"], wl["n"] - m, wl["dv"], wl["dc"], eps, RUN_SEED, s * fpp * 0, fpp,
-                             wl["cap"], wl["expurgation"], nthreads=cores, return_seconds=True)
+        c, dsec = chk.mc_run(vl, cl, n, n - m, dv, dc, eps, RUN_SEED + s, 0, fpp, cap, wl["expurgation"], nthreads=cores,
+                             return_seconds=True)
         if s >= args.warmup:
             secs.append(dsec)
-            frames += int(c[:, wl["cap"] + 3].sum())
-            execs += int(c[:, wl["cap"] + 5].sum())
+            frames += int(c[:, cap + 3].sum())
+            execs += int(c[:, cap + 5].sum())
     total = sum(secs)
     value = frames / total
-    eu = execs * wl["n"] * wl["dv"] / total
-    sample = f"{fpp} frames/point x {len(eps)} points per step, decode calls only, {cores} threads"
+    eu = execs * n * dv / total
+    sample = (f"{fpp} frames/point x {len(eps)} points per step, unmodified message_passing.c (gcc -O2) in a C frame loop, "
+              f"decode calls only, {cores} threads")
     if wl.get("ensemble"):
         sample += " (one fixed graph: the reference's per-frame graph generation, 2-3 s per (4,8) n=2000 graph, is NOT timed)"
     line = {"impl": "reference", "metric": "decoded frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "edge_updates_per_s": eu,
-            "config": {"workload": args.workload + ": " + wl["desc"], "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "edge_updates_per_s": eu, "config": config_of(args.workload, wl, args.scaling),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
                              "edge_updates_per_s": eu},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -143,13 +196,205 @@ def run_reference(args, wl):
     _emit(line)
 
 
-def run_ensemble(args, wl, L, D, torch, tdist, rank, world, local, dev):
-    """Ensemble workloads (a fresh random graph per frame group, generated inside the kernel): the public entry
-    point is the synchronous host-buffer call ldpc_b200_mc_run_ensemble, so `value` and `e2e` are the same
-    measurement (host eps in, host counter block out, every step)."""
+# ------------------------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------------------------
+class Env:
+    pass
+
+
+def smem_peak(L, local, clocks_mhz):
+    """Roofline denominator of the shared-memory engine: measured on this GPU (conflict-free LDS.128 from every SM,
+    exactly 16 volatile loads per thread and iteration) and cross-checked against the physical ceiling
+    148 SM x 128 B/clk x SM clock -- a probe above the ceiling is a broken probe, not a faster GPU."""
+    measured = L.api.smem_bandwidth_gbs(local)
+    sms = 148
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+    except Exception:
+        pass
+    nominal = sms * SMEM_NOMINAL_B_PER_CLK_SM * (clocks_mhz or 1965.0) * 1e6 / 1e9
+    return {"measured_gbs": measured, "nominal_gbs": nominal, "used_gbs": min(measured, nominal) if measured > 0 else nominal,
+            "source": "ldpc_b200_smem_probe (LDS.128, all SMs), capped at SMs x 128 B/clk x sampled SM clock"}
+
+
+def measure_fixed(E, name, wl, steps, warmup, with_cpu, cold=True):
+    """One workload on a fixed graph through mc_launch (device-resident `value`) and mc_run (host-buffer `e2e`)."""
+    torch, L, D, tdist = E.torch, E.L, E.D, E.tdist
+    rank, world, local, dev = E.rank, E.world, E.local, E.dev
+    n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
+    npoints = len(eps)
+    frames = wl["frames"]
+    strong = E.scaling == "strong"
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def my_range(step):
+        """(first_frame, count) of this rank for one step; frames are keyed by their global index"""
+        if strong:
+            return D.shard_frames(frames, rank, world, first_frame=0)
+        return rank * ((frames + 127) // 128 * 128), frames
+
+    vl, cl = L.generate_graph(n, dv, dc, seed=GRAPH_SEED, mode=1)
+
+    # ---- cold end-to-end: what the FIRST call of a fresh process costs (graph upload, placement search, pilot, module
+    # load) -- one step through the host-buffer API on a new handle, wall clock
+    cold_info = None
+    if cold:
+        barrier()
+        t0 = time.perf_counter()
+        g = L.Graph(vl, cl, device=local)
+        lo, cnt = my_range(0)
+        c = g.mc_run(eps, RUN_SEED + 999, cnt, cap, expurgation=wl["expurgation"], first_frame=lo) if cnt else None
+        barrier()
+        t_cold = time.perf_counter() - t0
+        tt = torch.tensor([t_cold], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        cold_frames = npoints * (frames if strong else frames * world)
+        cold_info = {"value": cold_frames / float(tt.item()), "unit": "frames/s", "seconds": float(tt.item()),
+                     "what": "fresh handle: graph upload + placement search (or its disk cache) + pilot + ONE step through "
+                             "ldpc_b200_mc_run with host buffers"}
+    else:
+        g = L.Graph(vl, cl, device=local)
+
+    d_cnt = torch.zeros((npoints, cap + 6), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(s):
+        flush.fill_(s & 0xFF)  # L2 flush between steps (the E1 working set is on-chip anyway)
+        d_cnt.zero_()
+        lo, cnt = my_range(s)
+        if cnt:
+            g.mc_launch(eps, RUN_SEED + s, cnt, cap, d_cnt.data_ptr(), stream, expurgation=wl["expurgation"], first_frame=lo)
+        D.allreduce_counters(d_cnt)
+
+    for s in range(warmup):
+        step(s)
+    barrier()
+    g.kernel_times_ms()
+    g.mc_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    acc = None
+    for s in range(steps):
+        step(warmup + s)
+        acc = d_cnt.clone() if acc is None else acc + d_cnt
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+    ms = float(ms.item())
+    cnt = acc.cpu().numpy().view(np.uint64)
+    tot_frames = int(cnt[:, cap + 3].sum())
+    tot_exec = int(cnt[:, cap + 5].sum())
+    kt = g.kernel_times_ms()
+    stats = g.mc_stats()
+    Ed = n * dv
+    value = tot_frames / (ms * 1e-3)
+
+    # ---- strong scaling: the N-GPU block of the last timed step must equal the 1-GPU block, bit for bit
+    strong_check = None
+    if strong and world > 1 and frames * n * npoints <= 4e12:
+        d1 = torch.zeros_like(d_cnt)
+        if rank == 0:
+            g.mc_launch(eps, RUN_SEED + warmup + steps - 1, frames, cap, d1.data_ptr(), stream,
+                        expurgation=wl["expurgation"], first_frame=0)
+            torch.cuda.synchronize()
+            strong_check = bool(torch.equal(d1, d_cnt))
+            assert strong_check, "strong scaling: the N-GPU counter block differs from the 1-GPU block"
+            g.kernel_times_ms(); g.mc_stats()
+        barrier()
+
+    # ---- roofline of the dominant kernel (this rank's launches; algorithmic bytes / measured duration)
+    b_alg = alg_bytes_per_edge_update(dv, dc, n)
+    per_rank_exec = tot_exec / world
+    k_ms = float(np.sum(kt)) / max(steps, 1) if len(kt) else float("nan")
+    alg_bytes_per_launch = per_rank_exec / steps * Ed * b_alg
+    achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9
+    is_e1 = stats["engine"] == 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sp = smem_peak(L, local, clocks["sm_mhz"] if clocks else None) if rank == 0 and is_e1 else None
+    peak = sp["used_gbs"] if (is_e1 and sp) else hbm_peak
+    spill_bytes = stats["spilled_records"] * stats["record_bytes"] * 2
+    roofline = {"bound": "smem" if is_e1 else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": spill_bytes / max(steps, 1) if is_e1 else None,
+                "traffic_note": ("DRAM bytes per step of the staged pipeline = spill records written + read back between stages "
+                                 "(spilled_records x record_bytes x 2, exact, from the kernels' own counters; ncu "
+                                 "dram__bytes of the stage-0 launch in profiles/ agrees); graph and state never leave the SM")
+                if is_e1 else "see profiles/ (ncu dram__bytes of the E2 launch)",
+                "peak_detail": sp if is_e1 else {"hbm_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+                "kernel": (("e1_mc_staged_kernel x%d stages (survivor re-packing), timed as one pipeline" % stats["stages"])
+                           if stats["stages"] > 1 else "e1_mc_kernel") if is_e1 else "e2_kernel",
+                "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms * steps / ms,
+                "alg_bytes_per_edge_update": b_alg, "alg_bytes_per_launch": alg_bytes_per_launch,
+                "frac_of_hbm_peak": achieved / hbm_peak,
+                "lane_inflation": stats["phys_frame_iterations"] / max(per_rank_exec, 1)}
+
+    # ---- end to end through the public host-buffer API (eps H2D + counters D2H per step, existing handle)
+    e2e_frames = 0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        lo, cntf = my_range(s)
+        if cntf:
+            c = g.mc_run(eps, RUN_SEED + 1000 + s, cntf, cap, expurgation=wl["expurgation"], first_frame=lo)
+            e2e_frames += int(c[:, cap + 3].sum())
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0, float(e2e_frames)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tt = t_e2e.clone()
+        tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        fsum = t_e2e.clone()
+        tdist.all_reduce(fsum, op=tdist.ReduceOp.SUM)
+        t_e2e = torch.stack([tt[0], fsum[1]])
+    e2e = {"value": float(t_e2e[1].item()) / float(t_e2e[0].item()), "unit": "frames/s",
+           "h2d_bytes_per_step": int(npoints * 16), "d2h_bytes_per_step": int(npoints * (cap + 6) * 8)}
+    if cold_info:
+        e2e["cold"] = cold_info
+
+    out = {"value": value, "unit": "frames/s", "ms_per_step": ms / steps, "edge_updates_per_s": tot_exec * Ed / (ms * 1e-3),
+           "config": config_of(name, wl, E.scaling), "engine": stats, "roofline": roofline, "e2e": e2e,
+           "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks,
+           "timing": {"l2": "256 MiB flush write between steps", "events": "torch.cuda.Event on the launch stream, max over ranks"}}
+    if strong_check is not None:
+        out["strong_scaling_counters_equal_single_gpu"] = strong_check
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_baseline(wl, vl, cl, with_variants=(name != "c3"),
+                                           got_fn=lambda fpp: g.mc_run(eps, RUN_SEED, fpp, cap, expurgation=wl["expurgation"]))
+    g.close()
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_ensemble(E, name, wl, steps, warmup):
+    """Ensemble workloads (a fresh random graph per frame group, generated inside the kernel): the public entry point is
+    the synchronous host-buffer call ldpc_b200_mc_run_ensemble, so `value` and `e2e` are the same measurement."""
+    torch, L, D, tdist = E.torch, E.L, E.D, E.tdist
+    rank, world, local, dev = E.rank, E.world, E.local, E.dev
     n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
     fpg = wl["frames_per_graph"]
     graphs = max(1, wl["frames"] // fpg)
+    strong = E.scaling == "strong"
+    my_graphs = graphs if not strong else (graphs * (rank + 1) // world - graphs * rank // world)
+    my_first = (lambda s: (s * world + rank) * graphs) if not strong else (lambda s: s * graphs + graphs * rank // world)
     npoints = len(eps)
 
     def barrier():
@@ -158,64 +403,53 @@ def run_ensemble(args, wl, L, D, torch, tdist, rank, world, local, dev):
         torch.cuda.synchronize()
 
     def step(s):
-        c, st = L.mc_run_ensemble(n, dv, dc, eps, RUN_SEED + s, graphs, cap, frames_per_graph=fpg, graph_seed=GRAPH_SEED,
-                                  gen_mode=2, first_graph=(s * world + rank) * graphs, expurgation=wl["expurgation"],
+        c, st = L.mc_run_ensemble(n, dv, dc, eps, RUN_SEED + s, my_graphs, cap, frames_per_graph=fpg, graph_seed=GRAPH_SEED,
+                                  gen_mode=2, first_graph=my_first(s), expurgation=wl["expurgation"],
                                   device=local, return_stats=True)
         t = torch.from_numpy(c.view(np.int64).copy()).to(dev)
         D.allreduce_counters(t)
         return t, st
 
-    for s in range(args.warmup):
+    for s in range(warmup):
         step(s)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     t0 = time.perf_counter()
-    acc, stats = None, None
-    phys = 0
-    for s in range(args.steps):
-        t, stats = step(args.warmup + s)
+    acc, stats, phys = None, None, 0
+    for s in range(steps):
+        t, stats = step(warmup + s)
         acc = t if acc is None else acc + t
         phys += stats["phys_frame_iterations"]
-    e1.record()
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
+    ms = torch.tensor([wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
     ms = float(ms.item())
-    if rank != 0:
-        return
     cnt = acc.cpu().numpy().view(np.uint64)
     tot_frames, tot_exec = int(cnt[:, cap + 3].sum()), int(cnt[:, cap + 5].sum())
-    E = n * dv
+    Ed = n * dv
     value = tot_frames / (ms * 1e-3)
     b_alg = alg_bytes_per_edge_update(dv, dc, n)
-    smem_peak = L.api.smem_bandwidth_gbs(local)
-    achieved = tot_exec / world * E * b_alg / (ms * 1e-3) / 1e9
-    line = {"metric": "decoded frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "edge_updates_per_s": tot_exec * E / (ms * 1e-3),
-            "graphs_per_s": npoints * graphs * world * args.steps / (ms * 1e-3),
-            "config": {"workload": args.workload + ": " + wl["desc"], "graphs_per_point_per_gpu": graphs,
-                       "frames_per_graph": fpg, "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED,
-                       "l2": "working set is on-chip (graph, state and generator scratch in shared memory)", "engine": stats},
-            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
-                         "traffic": None, "kernel": "e1_mc_kernel (ensemble: graph generation + decode), whole call timed",
-                         "alg_bytes_per_edge_update": b_alg,
-                         "lane_inflation": phys * world / max(tot_exec, 1),
+    sp = smem_peak(L, local, clocks["sm_mhz"] if clocks else None) if rank == 0 else {"used_gbs": 1.0}
+    achieved = tot_exec / world * Ed * b_alg / (ms * 1e-3) / 1e9
+    return {"value": value, "unit": "frames/s", "ms_per_step": ms / steps, "edge_updates_per_s": tot_exec * Ed / (ms * 1e-3),
+            "graphs_per_s": npoints * graphs * (1 if strong else world) * steps / (ms * 1e-3),
+            "config": config_of(name, wl, E.scaling), "engine": stats,
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": sp["used_gbs"], "unit": "GB/s", "frac": achieved / sp["used_gbs"],
+                         "traffic": 0, "peak_detail": sp,
+                         "kernel": "e1_mc_kernel (ensemble: graph generation + decode), whole host call timed",
+                         "alg_bytes_per_edge_update": b_alg, "lane_inflation": phys * world / max(tot_exec, 1),
                          "note": "graph generation and the expurgation second pass are inside the timed call and carry no "
                                  "algorithmic bytes"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": int(npoints * 8),
                     "d2h_bytes_per_step": int(npoints * (cap + 6) * 8)},
-            "gpu_launches": int(stats["kernel_launches"]) * args.steps, "clocks": clocks}
-    _emit(line)
-    if world > 1:
-        tdist.destroy_process_group()
+            "gpu_launches": int(stats["kernel_launches"]) * steps, "clocks": clocks,
+            "timing": {"l2": "working set is on-chip (graph, state and generator scratch in shared memory)",
+                       "events": "host wall clock around the synchronous calls, max over ranks"}}
 
 
 _REAL_STDOUT = None
@@ -244,10 +478,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="frames per point per GPU per step (default: workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per point per step (default: workload's)")
     ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per point per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra-c1", action="store_true", help="also report n=1000 steady-state frames/s")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra c1 (n=1000) and c3 (n=10^6) legs")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold (fresh handle) end-to-end measurement")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
@@ -258,175 +494,36 @@ def main():
     import torch
     import iib_project_ldpc_codes_b200 as L
     from iib_project_ldpc_codes_b200 import dist as D
+    import torch.distributed as tdist
 
-    rank, world, local = D.init_from_env()
+    E = Env()
+    E.torch, E.L, E.D, E.tdist = torch, L, D, tdist
+    E.rank, E.world, E.local = D.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    import torch.distributed as tdist
+    torch.cuda.set_device(E.local)
+    E.dev = torch.device("cuda", E.local)
+    E.scaling = args.scaling
+
     if wl.get("ensemble"):
-        return run_ensemble(args, wl, L, D, torch, tdist, rank, world, local, dev)
+        res = measure_ensemble(E, args.workload, wl, args.steps, args.warmup)
+    else:
+        res = measure_fixed(E, args.workload, wl, args.steps, args.warmup, with_cpu=not args.no_cpu_baseline,
+                            cold=not args.no_cold)
+    line = {"metric": "decoded frames/s", "n_gpus": E.world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic"}
+    line.update(res)
 
-    def barrier():
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
-
-    n, dv, dc, cap, eps = wl["n"], wl["dv"], wl["dc"], wl["cap"], wl["eps"]
-    vl, cl = L.generate_graph(n, dv, dc, seed=GRAPH_SEED, mode=1)
-    g = L.Graph(vl, cl, device=local)
-    # the handle is reused for every step: let the one-time bank-conflict placement search run longer (public knob)
-    place_effort = max(6, min(24, 24000 // n))
-    g.set_place_effort(place_effort)
-    frames = wl["frames"]
-    npoints = len(eps)
-    d_cnt = torch.zeros((npoints, cap + 6), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step(s):
-        flush.fill_(s & 0xFF)  # L2 flush between steps (the kernel's working set is on-chip anyway)
-        d_cnt.zero_()
-        g.mc_launch(eps, RUN_SEED + s, frames, cap, d_cnt.data_ptr(), stream, expurgation=wl["expurgation"],
-                    first_frame=rank * ((frames + 127) // 128 * 128))
-        D.allreduce_counters(d_cnt)
-
-    for s in range(args.warmup):
-        step(s)
-    barrier()
-    g.kernel_times_ms()
-    g.mc_stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot_frames = tot_exec = 0
-    barrier()
-    e0.record()
-    for s in range(args.steps):
-        step(args.warmup + s)
-        # counters of the step are consumed after the loop for the last step; accumulate on device
-        if s == 0:
-            acc = d_cnt.clone()
-        else:
-            acc += d_cnt
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
-    ms = float(ms.item())
-    cnt = acc.cpu().numpy().view(np.uint64)
-    tot_frames = int(cnt[:, cap + 3].sum())
-    tot_exec = int(cnt[:, cap + 5].sum())
-    kt = g.kernel_times_ms()
-    stats = g.mc_stats()
-    E = n * dv
-    value = tot_frames / (ms * 1e-3)
-    eu_per_s = tot_exec * E / (ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (this rank's launches; algorithmic bytes / measured duration)
-    b_alg = alg_bytes_per_edge_update(dv, dc, n)
-    per_rank_exec = tot_exec / world
-    k_ms = float(np.mean(kt)) if len(kt) else float("nan")
-    alg_bytes_per_launch = per_rank_exec / args.steps * E * b_alg
-    achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9
-    smem_peak = L.api.smem_bandwidth_gbs(local)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    e1 = stats["engine"] == 1
-    roofline = {"bound": "smem" if e1 else "hbm", "achieved": achieved, "peak": smem_peak if e1 else hbm_peak,
-                "unit": "GB/s", "frac": achieved / (smem_peak if e1 else hbm_peak), "traffic": None,
-                "note": ("E1 keeps graph+state in shared memory: HBM sees only the counter REDs and the spill records of the "
-                         "staged pipeline (ncu, profiles/r1j_e1_staged_c2_w64_stage0_ncu_full.txt: 1.7 MB read + 0.51 GB written "
-                         "by the stage-0 launch of 1.2*10^6 frames, 5*10^-4 of its algorithmic shared-memory bytes); peak = "
-                         "shared-memory read bandwidth measured on this GPU by ldpc_b200_smem_probe (conflict-free LDS.128 "
-                         "from all SMs)")
-                if e1 else "E2 streams frame-minor state rows and int32 lookups from HBM/L2; peak = measured HBM copy bandwidth",
-                "kernel": (("e1_mc_staged_kernel x%d stages (survivor re-packing), timed as one pipeline" % stats["stages"])
-                           if stats["stages"] > 1 else "e1_mc_kernel") if e1 else "e2_kernel",
-                "kernel_ms_mean": k_ms,
-                "kernel_share_of_step": k_ms * args.steps / ms,
-                "alg_bytes_per_edge_update": b_alg, "alg_bytes_per_launch": alg_bytes_per_launch,
-                "frac_of_hbm_peak": achieved / hbm_peak, "hbm_peak": hbm_peak,
-                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "lane_inflation": stats["phys_frame_iterations"] / max(per_rank_exec, 1)}
-
-    # ---- end to end through the public host-buffer API (graph upload + eps H2D + counters D2H per step)
-    e2e_frames = 0
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        # the call a user makes per batch: host eps in, host counter block out, on an existing graph handle
-        c = g.mc_run(eps, RUN_SEED + 1000 + s, frames, cap, expurgation=wl["expurgation"],
-                     first_frame=rank * ((frames + 127) // 128 * 128))
-        e2e_frames += int(c[:, cap + 3].sum())
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        tdist.all_reduce(t_e2e, op=tdist.ReduceOp.MAX)
-    e2e = {"value": e2e_frames * world / float(t_e2e.item()), "unit": "frames/s",
-           "h2d_bytes_per_step": int(npoints * 16),
-           "d2h_bytes_per_step": int(npoints * (cap + 6) * 8)}
-
-    if rank != 0:
-        return
-    line = {"metric": "decoded frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "edge_updates_per_s": eu_per_s,
-            "config": {"workload": args.workload + ": " + wl["desc"], "frames_per_point_per_gpu": frames,
-                       "graph_seed": GRAPH_SEED, "run_seed": RUN_SEED, "l2": "256 MiB flush write between steps",
-                       "place_effort": place_effort, "engine": stats},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]), "clocks": clocks}
-
-    if not args.no_cpu_baseline and world >= 1:
-        from oracle import oracle as O
-        cores = os.cpu_count() or 1
-        chk = O.best()
-        fpp = max(cores * max(1, int(64 * 10000 / n)), 1 if n > 100000 else 32)
-        c, dsec = chk.mc_run(vl, cl, n, g.k, dv, dc, eps, RUN_SEED, 0, fpp, cap, wl["expurgation"], nthreads=cores,
-                             return_seconds=True)
-        v = int(c[:, cap + 3].sum()) / dsec
-        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores,
-                                "kind": "reference" if O.have_ref() else "port",
-                                "sample": f"{fpp} frames/point x {npoints} points, decode calls only",
-                                "edge_updates_per_s": int(c[:, cap + 5].sum()) * E / dsec}
-        # the sample is also a live parity check of the GPU path on the same frames
-        got = g.mc_run(eps, RUN_SEED, fpp, cap, expurgation=wl["expurgation"])
-        line["cpu_baseline"]["parity_on_sample"] = bool(np.array_equal(got, c))
-
-    if args.extra_c1 or args.workload == "c2":
-        w1 = WORKLOADS["c1"]
-        v1, c1 = L.generate_graph(w1["n"], 3, 6, seed=GRAPH_SEED, mode=1)
-        g1 = L.Graph(v1, c1, device=local)
-        g1.set_place_effort(24)
-        f1 = 20_000_000
-        d1 = torch.zeros((1, w1["cap"] + 6), dtype=torch.int64, device=dev)
-        for _ in range(2):
-            g1.mc_launch(w1["eps"], RUN_SEED, f1, w1["cap"], d1.data_ptr(), stream)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d1.zero_()
-        a0.record()
-        g1.mc_launch(w1["eps"], RUN_SEED + 1, f1, w1["cap"], d1.data_ptr(), stream)
-        a1.record()
-        torch.cuda.synchronize()
-        t1 = a0.elapsed_time(a1) * 1e-3
-        c1n = d1.cpu().numpy().view(np.uint64)
-        line["extra_n1000"] = {"workload": w1["desc"].replace("10^8", "2*10^7"), "frames_per_s_per_gpu": f1 / t1,
-                               "edge_updates_per_s_per_gpu": int(c1n[0, w1["cap"] + 5]) * 3000 / t1,
-                               "roofline_frac_smem": int(c1n[0, w1["cap"] + 5]) * 3000 / t1 *
-                               alg_bytes_per_edge_update(3, 6, 1000) / 1e9 / smem_peak,
-                               "engine": g1.mc_stats()}
-    _emit(line)
-    if world > 1:
+    # extra legs (single GPU, default workload only): the configuration north_star's 10^9 frames/s target is quoted
+    # on, and the HBM-streamed n = 10^6 engine -- measured exactly like the main line
+    if E.world == 1 and args.workload == "c2" and not args.no_legs and not args.frames:
+        legs = {}
+        legs["c1"] = measure_fixed(E, "c1", dict(WORKLOADS["c1"]), steps=10, warmup=3, with_cpu=not args.no_cpu_baseline)
+        legs["c3"] = measure_fixed(E, "c3", dict(WORKLOADS["c3"]), steps=3, warmup=3, with_cpu=False, cold=False)
+        line["legs"] = legs
+    if E.rank == 0:
+        _emit(line)
+    if E.world > 1:
         tdist.destroy_process_group()
 
 

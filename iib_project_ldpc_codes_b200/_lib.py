@@ -30,7 +30,9 @@ class LdpcB200Error(RuntimeError):
 class McStats(ct.Structure):
     _fields_ = [("phys_frame_iterations", ct.c_uint64), ("second_pass_groups", ct.c_uint64),
                 ("engine", ct.c_int32), ("words", ct.c_int32), ("teams", ct.c_int32), ("team_warps", ct.c_int32),
-                ("grid", ct.c_int32), ("smem_bytes", ct.c_int32), ("stages", ct.c_int32), ("kernel_launches", ct.c_int32)]
+                ("grid", ct.c_int32), ("smem_bytes", ct.c_int32), ("stages", ct.c_int32), ("kernel_launches", ct.c_int32),
+                ("spilled_records", ct.c_uint64), ("recounted_frames", ct.c_uint64), ("record_bytes", ct.c_int32),
+                ("tmem_lists", ct.c_int32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -40,7 +42,7 @@ class McStats(ct.Structure):
 EXPORTS = [
     "message_passing", "generate_random_code", "ldpc_b200_last_error", "ldpc_b200_device_count",
     "ldpc_b200_generate_graph", "ldpc_b200_graph_create", "ldpc_b200_graph_destroy", "ldpc_b200_counters_len",
-    "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
+    "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_launch_points", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
     "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning", "ldpc_b200_smem_probe",
     "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble", "ldpc_b200_generate_graph_indexed",
 ]
@@ -86,6 +88,9 @@ def load() -> ct.CDLL:
     lib.ldpc_b200_mc_launch.restype = ct.c_int
     lib.ldpc_b200_mc_launch.argtypes = [ct.c_void_p, P_F64, ct.c_int, ct.c_uint64, ct.c_uint64, ct.c_uint64, ct.c_int,
                                         ct.c_int, ct.c_void_p, ct.c_void_p]
+    lib.ldpc_b200_mc_launch_points.restype = ct.c_int
+    lib.ldpc_b200_mc_launch_points.argtypes = [ct.c_void_p, P_F64, ct.c_int, ct.c_uint32, ct.c_uint64, ct.c_uint64, ct.c_uint64,
+                                               ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p]
     lib.ldpc_b200_mc_stats_read.restype = ct.c_int
     lib.ldpc_b200_mc_stats_read.argtypes = [ct.c_void_p, ct.POINTER(McStats)]
     lib.ldpc_b200_kernel_times.restype = ct.c_int

@@ -155,6 +155,15 @@ class Graph:
                                             iterations, expurgation, ct.c_void_p(d_counters_ptr),
                                             ct.c_void_p(stream_ptr)))
 
+    def mc_launch_point(self, eps_p, point, seed, num_frames, iterations, d_counters_ptr, stream_ptr=0, expurgation=-1,
+                        first_frame=0):
+        """One erasure point of a longer list, keyed as point index `point` (ldpc_b200_mc_launch_points): ADDS into the
+        device row [iterations+6] at d_counters_ptr."""
+        eps = np.ascontiguousarray([eps_p], dtype=np.float64)
+        check(self._lib.ldpc_b200_mc_launch_points(self._h, ptr(eps, P_F64), 1, point, seed, first_frame, num_frames,
+                                                   iterations, expurgation, ct.c_void_p(d_counters_ptr),
+                                                   ct.c_void_p(stream_ptr)))
+
     def mc_stats(self):
         st = McStats()
         check(self._lib.ldpc_b200_mc_stats_read(self._h, ct.byref(st)))

@@ -115,6 +115,7 @@ struct E1Params {
     uint32_t draw_qcap;   // test hook: cap on the continuation queue of team_draw (0 = as large as `two` allows)
     uint32_t seed_lo, seed_hi;   // run seed (same in every bec[p]); a kernel parameter so the Philox round keys are uniform
     int npoints, cap, expurgation;
+    uint32_t point0;                    // erasure point p of this launch is keyed as point0 + p by the channel generator
     unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
     unsigned long long num_frames;      // frames per point
     unsigned long long groups_per_point;
@@ -744,9 +745,9 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
     // draw the erasure pattern (channels.py:24-26) straight into shared memory
     uint32_t red[WORDS];
     if (P.recount)
-        team_draw_lanes<WORDS, MASKED>(P, t, bp, point, t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS + 8, valid, mask, x, red, cnt);
+        team_draw_lanes<WORDS, MASKED>(P, t, bp, point + P.point0, t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS + 8, valid, mask, x, red, cnt);
     else
-        team_draw<WORDS, MASKED>(P, t, bp, point, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
+        team_draw<WORDS, MASKED>(P, t, bp, point + P.point0, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
                                  t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
     team_reduce<WORDS>(t, red, cnt);
     LDPC_FORW any[w] = red[w];

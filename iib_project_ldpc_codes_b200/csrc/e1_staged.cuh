@@ -54,6 +54,7 @@ struct StageParams {
     int exp_mode;
     uint32_t* id_list;                    // [npoints][point_stride]
     unsigned long long* id_cnt;           // [npoints] (atomic)
+    unsigned long long* stats;            // handle statistics: [2] += spilled records, [3] += listed frames
 };
 
 // Everything after a group's iterations [lo, age): which frames are deferred to the next stage, the residual of the
@@ -115,6 +116,7 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
             if (t.tid == 0) {
                 const unsigned long long v = atomicAdd(S.id_cnt + point, (unsigned long long)nemit);
                 work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+                if (S.stats) atomicAdd(S.stats + 3, (unsigned long long)nemit);
             }
             team_sync(t);
             const unsigned long long ebase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
@@ -134,12 +136,16 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
         unsigned long long sbase;
         if (t.team_warps == 1) {
             unsigned long long v = 0;
-            if (t.lane == 0) v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+            if (t.lane == 0) {
+                v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
+                if (S.stats) atomicAdd(S.stats + 2, (unsigned long long)ndef);
+            }
             sbase = __shfl_sync(0xFFFFFFFFu, v, 0);
         } else {
             if (t.tid == 0) {
                 unsigned long long v = atomicAdd(S.cnt_out + point, (unsigned long long)ndef);
                 work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
+                if (S.stats) atomicAdd(S.stats + 2, (unsigned long long)ndef);
             }
             team_sync(t);
             sbase = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
@@ -276,7 +282,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             const BecParams bp = P.bec[point];
             const unsigned long long q0 = P.first_word + gi * WORDS;
             uint32_t red[WORDS];
-            team_draw<WORDS, false>(P, t, bp, point, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
+            team_draw<WORDS, false>(P, t, bp, point + P.point0, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
                                     t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
             if (S.exp_mode)
                 for (int f = t.tid; f < W; f += t.nthr) fid[f] = (uint32_t)(gi * W + f);

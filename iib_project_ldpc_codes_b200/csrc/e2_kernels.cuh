@@ -40,6 +40,7 @@ struct E2Params {
     // Monte-Carlo
     const BecParams* bec;
     int npoints, cap, expurgation;
+    uint32_t point0;   // erasure point p of this launch is keyed as point0 + p by the channel generator
     unsigned long long first_word, num_frames, batches_per_point;
     unsigned long long* counters;   // raw layout of e1_kernels.cuh
     // decode
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant
                     uint4 xi;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const uint32_t wv = bec_word(bp, point, q0 + q * 4 + k, (uint32_t)i) & s_valid[q * 4 + k];
+                        const uint32_t wv = bec_word(bp, point + P.point0, q0 + q * 4 + k, (uint32_t)i) & s_valid[q * 4 + k];
                         q_at(xi, k) = wv;
                         q_at(any, k) |= wv;
                         cnt0 += __popc(wv & s_mask[q * 4 + k]);

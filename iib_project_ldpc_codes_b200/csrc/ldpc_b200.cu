@@ -13,6 +13,9 @@
 #include <vector>
 #include <unordered_map>
 #include <algorithm>
+#include <utility>
+#include <new>
+#include <exception>
 
 #include "../../include/ldpc_b200.h"
 #include "e1_kernels.cuh"
@@ -43,6 +46,16 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* ldpc_b200_last_error(void) { return g_last_error.c_str(); }
 
+// No C++ exception may cross the C ABI (a std::bad_alloc from a host-side planner would otherwise terminate the
+// caller's process): every entry point that allocates runs its body through this.
+template <class F>
+static int guarded(const char* what, F&& body) {
+    try { return body(); }
+    catch (const std::bad_alloc&) { return fail(LDPC_B200_ENOMEM, "%s: out of host memory", what); }
+    catch (const std::exception& e) { return fail(LDPC_B200_EINVAL, "%s: %s", what, e.what()); }
+    catch (...) { return fail(LDPC_B200_EINVAL, "%s: unknown C++ exception", what); }
+}
+
 extern "C" int ldpc_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -70,6 +83,16 @@ struct StagePlan {
     double predicted_inflation = 0;
     unsigned long long pilot_frames = 0;   // frames per point the pilot decoded (a much larger run draws a better one)
     double pilot_fer = 0;                  // largest block error rate over the points, as the pilot saw it
+    int* d_cuts = nullptr;                 // device copy of `cuts`, uploaded once when the plan is made
+    StagePlan() = default;
+    StagePlan(const StagePlan&) = delete;
+    StagePlan(StagePlan&& o) noexcept { *this = std::move(o); }
+    StagePlan& operator=(StagePlan&& o) noexcept {
+        nstages = o.nstages; cuts = std::move(o.cuts); predicted_inflation = o.predicted_inflation;
+        pilot_frames = o.pilot_frames; pilot_fer = o.pilot_fer; std::swap(d_cuts, o.d_cuts);
+        return *this;
+    }
+    ~StagePlan() { if (d_cuts) cudaFree(d_cuts); }
 };
 
 struct ldpc_b200_graph {
@@ -99,7 +122,6 @@ struct ldpc_b200_graph {
     void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0;
     uint32_t* d_idlist = nullptr; size_t idlist_bytes = 0;   // expurgated runs: frames listed for the re-count pass
     unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
-    int* d_cuts = nullptr; size_t cuts_cap = 0;
     // batched decode buffers (cached between calls)
     void* dec_mvc = nullptr; void* dec_x = nullptr; void* dec_v = nullptr; void* dec_err = nullptr; void* dec_ret = nullptr;
     size_t dec_mvc_cap = 0, dec_x_cap = 0, dec_v_cap = 0, dec_err_cap = 0, dec_ret_cap = 0;
@@ -109,11 +131,15 @@ struct ldpc_b200_graph {
     unsigned long long* d_work = nullptr;
     unsigned long long* d_raw = nullptr; size_t raw_cap = 0;
     BecParams* d_bec = nullptr; int bec_cap = 0;
+    // erasure-point parameters go up through a small ring of pinned host slots (no synchronisation in mc_launch:
+    // a slot is reused only after the copy that read it has completed)
+    static constexpr int BEC_RING = 8;
+    BecParams* h_bec[BEC_RING] = {}; int h_bec_cap[BEC_RING] = {}; cudaEvent_t h_bec_ev[BEC_RING] = {}; int h_bec_next = 0;
     unsigned long long* d_out = nullptr; size_t out_cap = 0;  // for mc_run
     // tuning overrides
     int tune_words = 0, tune_teams = 0, tune_team_warps = 0;
     // statistics of launches since last read
-    unsigned long long* d_stats = nullptr;  // [2]: phys frame-iterations, second-pass groups
+    unsigned long long* d_stats = nullptr;  // [4]: phys frame-iterations, second-pass groups, spilled records, re-counted frames
     ldpc_b200_mc_stats last = {};
     // kernel timing ring
     static constexpr int RING = 256;
@@ -263,7 +289,7 @@ static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int k, int dv, int dc, int device,
+static int ldpc_b200_graph_create_impl(const int* v2c, const int* c2v, int n, int k, int dv, int dc, int device,
                                       ldpc_b200_graph** out) {
     if (!out) return fail(LDPC_B200_EINVAL, "graph_create: out is NULL");
     *out = nullptr;
@@ -313,23 +339,29 @@ extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int
     }
     {
         cudaError_t e = cudaMalloc(&g->d_work, sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMalloc(&g->d_stats, 2 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&g->d_stats, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, 4 * sizeof(unsigned long long));
         if (e != cudaSuccess) { ldpc_b200_graph_destroy(g); return fail(LDPC_B200_ECUDA, "graph_create: %s", cudaGetErrorString(e)); }
     }
     *out = g;
     return LDPC_B200_OK;
 }
+extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int k, int dv, int dc, int device,
+                                      ldpc_b200_graph** out) {
+    return guarded("graph_create", [&] { return ldpc_b200_graph_create_impl(v2c, c2v, n, k, dv, dc, device, out); });
+}
+
 
 extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
     cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
+    for (int i = 0; i < ldpc_b200_graph::BEC_RING; i++) { if (g->h_bec[i]) cudaFreeHost(g->h_bec[i]); if (g->h_bec_ev[i]) cudaEventDestroy(g->h_bec_ev[i]); }
     for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
     cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
     cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
-    cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_cuts); cudaFree(g->d_idlist);
+    cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_idlist);
     cudaFree(g->dec_mvc); cudaFree(g->dec_x); cudaFree(g->dec_v); cudaFree(g->dec_err); cudaFree(g->dec_ret);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
@@ -514,11 +546,12 @@ struct DevBuf {
 #include "e2_host.inc"
 #include "e1_staged_host.inc"
 
-extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int npoints, uint32_t first_point, uint64_t seed,
                                    uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
                                    uint64_t* d_counters, void* stream) {
     if (!g || !eps || !d_counters) return fail(LDPC_B200_EINVAL, "mc_launch: NULL argument");
-    if (npoints <= 0 || npoints >= (1 << 24)) return fail(LDPC_B200_EINVAL, "mc_launch: npoints out of range");
+    if (npoints <= 0 || npoints >= (1 << 24) || (unsigned long long)first_point + (unsigned)npoints > (1u << 24))
+        return fail(LDPC_B200_EINVAL, "mc_launch: npoints / first_point out of range (the generator keys 2^24 points)");
     if (iterations < 0 || iterations > 65535) return fail(LDPC_B200_EINVAL, "mc_launch: iterations out of range");
     if (first_frame % 128 != 0) return fail(LDPC_B200_EINVAL, "mc_launch: first_frame must be a multiple of 128");
     cudaStream_t st = (cudaStream_t)stream;
@@ -544,10 +577,21 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
         CUDA_TRY(cudaMalloc(&g->d_bec, sizeof(BecParams) * (size_t)npoints));
         g->bec_cap = npoints;
     }
-    std::vector<BecParams> hb(npoints);
-    for (int p = 0; p < npoints; p++) hb[p] = make_bec(eps[p], seed);
-    CUDA_TRY(cudaMemcpyAsync(g->d_bec, hb.data(), sizeof(BecParams) * (size_t)npoints, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));  // hb is a stack-lifetime pageable buffer
+    {
+        const int slot = g->h_bec_next;
+        g->h_bec_next = (slot + 1) % ldpc_b200_graph::BEC_RING;
+        if (!g->h_bec_ev[slot]) CUDA_TRY(cudaEventCreateWithFlags(&g->h_bec_ev[slot], cudaEventDisableTiming));
+        else CUDA_TRY(cudaEventSynchronize(g->h_bec_ev[slot]));   // the copy that last used this slot (8 launches ago)
+        if (g->h_bec_cap[slot] < npoints) {
+            if (g->h_bec[slot]) cudaFreeHost(g->h_bec[slot]);
+            g->h_bec[slot] = nullptr; g->h_bec_cap[slot] = 0;
+            CUDA_TRY(cudaMallocHost(&g->h_bec[slot], sizeof(BecParams) * (size_t)npoints));
+            g->h_bec_cap[slot] = npoints;
+        }
+        for (int p = 0; p < npoints; p++) g->h_bec[slot][p] = make_bec(eps[p], seed);
+        CUDA_TRY(cudaMemcpyAsync(g->d_bec, g->h_bec[slot], sizeof(BecParams) * (size_t)npoints, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(g->h_bec_ev[slot], st));
+    }
     CUDA_TRY(cudaMemsetAsync(g->d_raw, 0, raw_words * 8, st));
     CUDA_TRY(cudaMemsetAsync(g->d_work, 0, sizeof(unsigned long long), st));
 
@@ -557,7 +601,7 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
         const int slot2 = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
         if (slot2 >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot2], st));
         int grid2 = 0, R2 = 0;
-        rc2 = e2_mc(g, npoints, first_frame, num_frames, cap, expurgation, st, &grid2, &R2);
+        rc2 = e2_mc(g, npoints, first_point, first_frame, num_frames, cap, expurgation, st, &grid2, &R2);
         if (rc2) return rc2;
         if (slot2 >= 0) { CUDA_TRY(cudaEventRecord(g->ev1[slot2], st)); g->ev_count++; }
         e1_finalize_kernel<<<(npoints + 127) / 128, 128, 0, st>>>(g->d_raw, npoints, cap);
@@ -577,6 +621,7 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
     P.c2v = g->placed[cfg.words].d_c2v; P.v2c = g->placed[cfg.words].d_v2c; P.var_orig = g->placed[cfg.words].d_var_orig;
     const unsigned long long W = 32ull * cfg.words;
     P.bec = g->d_bec; P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.npoints = npoints; P.expurgation = expurgation;
+    P.point0 = first_point;
     P.first_word = first_frame / 32; P.num_frames = num_frames;
     P.groups_per_point = (num_frames + W - 1) / W;
     P.counters = g->d_raw; P.work_counter = g->d_work;
@@ -626,21 +671,39 @@ extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int np
 
     g->launches += 2;
     g->last.engine = 1; g->last.words = cfg.words; g->last.teams = cfg.teams; g->last.team_warps = cfg.team_warps;
-    g->last.grid = grid_used; g->last.smem_bytes = (int)cfg.smem;
+    g->last.grid = grid_used; g->last.smem_bytes = (int)cfg.smem; g->last.tmem_lists = cfg.tm ? 1 : 0;
+    g->last.record_bytes = plan ? 4 * (int)align_up((uint32_t)((g->n + 31) / 32) + (two_pass ? 1u : 0u), 4) : 0;
     return LDPC_B200_OK;
 }
+extern "C" int ldpc_b200_mc_launch(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+                                   uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                                   uint64_t* d_counters, void* stream) {
+    return guarded("mc_launch", [&] { return ldpc_b200_mc_launch_impl(g, eps, npoints, 0u, seed, first_frame, num_frames, iterations, expurgation, d_counters, stream); });
+}
+
+// The same launch for the erasure points [first_point, first_point + npoints) of a longer list: the channel generator
+// keys point p of this call as first_point + p, so a run may be split by POINT across GPUs or calls and
+// still decode exactly the frames of the unsplit run.  d_counters: [npoints][iterations+6] rows of THESE points.
+extern "C" int ldpc_b200_mc_launch_points(ldpc_b200_graph* g, const double* eps, int npoints, uint32_t first_point, uint64_t seed,
+                                          uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                                          uint64_t* d_counters, void* stream) {
+    return guarded("mc_launch_points", [&] { return ldpc_b200_mc_launch_impl(g, eps, npoints, first_point, seed, first_frame, num_frames, iterations, expurgation, d_counters, stream); });
+}
+
 
 #include "e1_ens_host.inc"
 
 extern "C" int ldpc_b200_mc_stats_read(ldpc_b200_graph* g, ldpc_b200_mc_stats* stats) {
     if (!g || !stats) return fail(LDPC_B200_EINVAL, "mc_stats_read: NULL argument");
     CUDA_TRY(cudaSetDevice(g->device));
-    unsigned long long h[2];
+    unsigned long long h[4];
     CUDA_TRY(cudaMemcpy(h, g->d_stats, sizeof h, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemset(g->d_stats, 0, sizeof h));
     *stats = g->last;
     stats->phys_frame_iterations = h[0];
     stats->second_pass_groups = h[1];
+    stats->spilled_records = h[2];
+    stats->recounted_frames = h[3];
     stats->stages = g->last_stages;
     stats->kernel_launches = g->launches;
     g->launches = 0;
@@ -659,7 +722,7 @@ extern "C" int ldpc_b200_kernel_times(ldpc_b200_graph* g, float* ms, int max) {
     return n;
 }
 
-extern "C" int ldpc_b200_mc_run(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+static int ldpc_b200_mc_run_impl(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
                                 uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
                                 uint64_t* counters, ldpc_b200_mc_stats* stats) {
     if (!g || !eps || !counters) return fail(LDPC_B200_EINVAL, "mc_run: NULL argument");
@@ -680,6 +743,12 @@ extern "C" int ldpc_b200_mc_run(ldpc_b200_graph* g, const double* eps, int npoin
     if (stats) return ldpc_b200_mc_stats_read(g, stats);
     return LDPC_B200_OK;
 }
+extern "C" int ldpc_b200_mc_run(ldpc_b200_graph* g, const double* eps, int npoints, uint64_t seed,
+                                uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                                uint64_t* counters, ldpc_b200_mc_stats* stats) {
+    return guarded("mc_run", [&] { return ldpc_b200_mc_run_impl(g, eps, npoints, seed, first_frame, num_frames, iterations, expurgation, counters, stats); });
+}
+
 
 // ------------------------------------------------------------------------------------------------
 template <bool VALUES>
@@ -715,7 +784,7 @@ static int grow(void** p, size_t* cap, size_t bytes) {
     return LDPC_B200_OK;
 }
 
-extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
+static int ldpc_b200_decode_batch_impl(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
                                       int* errors, int* ret) {
     if (!g || !Mvc || !ret || (!errors && iterations > 0)) return fail(LDPC_B200_EINVAL, "decode_batch: NULL argument");
     if (iterations < 0) return fail(LDPC_B200_EINVAL, "decode_batch: iterations < 0");
@@ -784,8 +853,13 @@ extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t 
     }
     return LDPC_B200_OK;
 }
+extern "C" int ldpc_b200_decode_batch(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
+                                      int* errors, int* ret) {
+    return guarded("decode_batch", [&] { return ldpc_b200_decode_batch_impl(g, Mvc, frames, iterations, errors, ret); });
+}
 
-extern "C" int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32_t point,
+
+static int ldpc_b200_draw_patterns_impl(int device, int n, double eps, uint64_t seed, uint32_t point,
                                        uint64_t first_frame, uint64_t frames, int8_t* out) {
     if (!out || n <= 0) return fail(LDPC_B200_EINVAL, "draw_patterns: bad argument");
     if (first_frame % 32 != 0) return fail(LDPC_B200_EINVAL, "draw_patterns: first_frame must be a multiple of 32");
@@ -805,6 +879,11 @@ extern "C" int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t s
     CUDA_TRY(cudaMemcpy(out, d_m.p, frames * n, cudaMemcpyDeviceToHost));
     return LDPC_B200_OK;
 }
+extern "C" int ldpc_b200_draw_patterns(int device, int n, double eps, uint64_t seed, uint32_t point,
+                                       uint64_t first_frame, uint64_t frames, int8_t* out) {
+    return guarded("draw_patterns", [&] { return ldpc_b200_draw_patterns_impl(device, n, eps, seed, point, first_frame, frames, out); });
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory bandwidth probe: the roofline denominator for the shared-memory-resident engine is
@@ -816,14 +895,18 @@ __global__ void __launch_bounds__(1024, 1) smem_probe_kernel(uint4* sink, int it
     for (int i = threadIdx.x; i < words; i += blockDim.x) s[i] = make_uint4(i, i * 3, i * 5, i * 7);
     __syncthreads();
     uint4 acc = make_uint4(0, 0, 0, 0);
-    int idx = threadIdx.x;
+    // exactly 16 LDS.128 per thread and iteration: volatile asm, so the compiler can neither merge two loads of the same
+    // address nor carry one across iterations (a carried load once made this probe report more than the 128 B/clk/SM
+    // the hardware has); lane l of a quarter warp reads bank quad l: conflict-free
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm) + (threadIdx.x & 1023u) * 16u;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            const uint4 v = s[(idx + k * 256) & (words - 1)];
+            uint4 v;
+            const uint32_t a = base + (uint32_t)(((k * 256 + it * 64) & 3071)) * 16u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
             acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
         }
-        idx = (idx + 1024) & (words - 1);
     }
     if (acc.x == 0x12345678u && acc.y == 1u) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
@@ -869,7 +952,7 @@ static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
     return h;
 }
 
-extern "C" int message_passing(int* Mvc, int iterations, int* variable_to_check_list, int* check_to_variable_list,
+static int message_passing_impl(int* Mvc, int iterations, int* variable_to_check_list, int* check_to_variable_list,
                                int* errors, int n, int k, int dv, int dc) {
     if (!Mvc || !variable_to_check_list || !check_to_variable_list || (!errors && iterations > 0))
         return fail(LDPC_B200_EINVAL, "message_passing: NULL argument");
@@ -949,3 +1032,8 @@ extern "C" int message_passing(int* Mvc, int iterations, int* variable_to_check_
     for (int i = 0; i < n; i++) Mvc[i] = frame[i];
     return it;
 }
+extern "C" int message_passing(int* Mvc, int iterations, int* variable_to_check_list, int* check_to_variable_list,
+                               int* errors, int n, int k, int dv, int dc) {
+    return guarded("message_passing", [&] { return message_passing_impl(Mvc, iterations, variable_to_check_list, check_to_variable_list, errors, n, k, dv, dc); });
+}
+

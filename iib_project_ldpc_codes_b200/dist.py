@@ -28,6 +28,42 @@ def shard_frames(num_frames: int, rank: int, world: int, first_frame: int = 0):
     return first_frame + lo, hi - lo
 
 
+def shard_items(npoints: int, num_frames: int, rank: int, world: int, first_frame: int = 0, blocks_per_point: int = 0):
+    """(point, block) partitioning -- SURVEY.md 8(e) "rank r takes (p, g) pairs", north_star "erasure-probability
+    points shard across the GPUs"; the reference's analogue is one OS process per (eps, code number) whose CSVs
+    tools/combine_data.py:64-95 re-weights and sums.
+
+    Every point's frame range is cut into `blocks_per_point` 128-aligned blocks (default: the smallest count that
+    gives every rank at least two items and makes npoints*blocks a multiple of `world`); item (b, p) has index
+    b*npoints + p and goes to rank index % world.  Returns this rank's [(point, first_frame, count), ...] with
+    consecutive blocks of a point merged.  Every (point, frame) belongs to exactly one rank, so the summed counter
+    blocks are bit-identical to a single-GPU run whatever the partitioning."""
+    if first_frame % ALIGN:
+        raise ValueError("first_frame must be a multiple of 128")
+    if blocks_per_point <= 0:
+        blocks_per_point = 1
+        while (npoints * blocks_per_point) % world or npoints * blocks_per_point < 2 * world:
+            blocks_per_point += 1
+    units = (num_frames + ALIGN - 1) // ALIGN
+    mine = []
+    for b in range(blocks_per_point):
+        for p in range(npoints):
+            if (b * npoints + p) % world != rank:
+                continue
+            lo = min(units * b // blocks_per_point * ALIGN, num_frames)
+            hi = min(units * (b + 1) // blocks_per_point * ALIGN, num_frames)
+            if hi > lo:
+                mine.append((p, first_frame + lo, hi - lo))
+    mine.sort()
+    merged = []
+    for p, lo, cnt in mine:
+        if merged and merged[-1][0] == p and merged[-1][1] + merged[-1][2] == lo:
+            merged[-1] = (p, merged[-1][1], merged[-1][2] + cnt)
+        else:
+            merged.append((p, lo, cnt))
+    return merged
+
+
 def init_from_env(backend: str | None = None):
     """torchrun-style rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*). Returns (rank, world, local_rank)."""
     import torch
@@ -56,19 +92,34 @@ def allreduce_counters(t):
     return t
 
 
-def sharded_mc_run(graph, eps, seed, num_frames, iterations, expurgation=-1, first_frame=0, rank=0, world=1):
-    """Decode this rank's share on its GPU and all-reduce; returns the GLOBAL uint64 counter block on the host."""
+def sharded_mc_run(graph, eps, seed, num_frames, iterations, expurgation=-1, first_frame=0, rank=0, world=1,
+                   partition="frames"):
+    """Decode this rank's share on its GPU and all-reduce; returns the GLOBAL uint64 counter block on the host.
+
+    partition "frames": a contiguous slice of EVERY point's frames (perfectly balanced: erasure points near the
+    threshold cost twice the iterations of points below it, and every rank gets the same mix) -- one launch;
+    partition "points": (point, block) items dealt round-robin (shard_items) -- one launch per item, each on a single
+    erasure point.  Both give bit-identical results."""
     import numpy as np
     import torch
 
-    lo, cnt = shard_frames(num_frames, rank, world, first_frame)
-    npoints = len(np.atleast_1d(eps))
+    eps = np.atleast_1d(np.asarray(eps, dtype=np.float64))
+    npoints = len(eps)
     dev = torch.device("cuda", graph.device)
     d = torch.zeros((npoints, iterations + 6), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        if cnt > 0:
-            graph.mc_launch(eps, seed, cnt, iterations, d.data_ptr(), torch.cuda.current_stream().cuda_stream,
-                            expurgation=expurgation, first_frame=lo)
+        stream = torch.cuda.current_stream().cuda_stream
+        if partition == "frames":
+            lo, cnt = shard_frames(num_frames, rank, world, first_frame)
+            if cnt > 0:
+                graph.mc_launch(eps, seed, cnt, iterations, d.data_ptr(), stream, expurgation=expurgation, first_frame=lo)
+        elif partition == "points":
+            for p, lo, cnt in shard_items(npoints, num_frames, rank, world, first_frame):
+                # the pattern of a frame is keyed by its point index: launch point p as point p
+                graph.mc_launch_point(float(eps[p]), p, seed, cnt, iterations, d[p].data_ptr(), stream,
+                                      expurgation=expurgation, first_frame=lo)
+        else:
+            raise ValueError("partition must be 'frames' or 'points'")
         allreduce_counters(d)
         out = d.cpu().numpy().view(np.uint64)
     return out

@@ -31,6 +31,7 @@ extern "C" {
 #define LDPC_B200_EINVAL      (-1)  /* bad argument / malformed graph / symbol outside {0,1,2} */
 #define LDPC_B200_ECUDA       (-2)  /* CUDA runtime failure (no device, launch error, out of memory) */
 #define LDPC_B200_EUNSUPPORTED (-3) /* configuration not supported by this build */
+#define LDPC_B200_ENOMEM      (-4)  /* out of host memory (no C++ exception ever crosses this ABI) */
 
 typedef struct ldpc_b200_graph ldpc_b200_graph;
 
@@ -45,6 +46,10 @@ typedef struct ldpc_b200_mc_stats {
     int32_t smem_bytes;             /* dynamic shared memory per CTA                                       */
     int32_t stages;                 /* stages of the last launch (survivor re-packing, 1 = unstaged)       */
     int32_t kernel_launches;        /* kernels launched since the previous statistics read                 */
+    uint64_t spilled_records;       /* frames written to (and read back from) the HBM spill buffers between stages */
+    uint64_t recounted_frames;      /* expurgated runs: frames listed by pass 1 and re-drawn by the re-count pass  */
+    int32_t record_bytes;           /* bytes per spill record: DRAM traffic = spilled_records * record_bytes * 2   */
+    int32_t tmem_lists;             /* 1 = socket lists in tensor memory (tcgen05.ld-supplied gather addresses)    */
 } ldpc_b200_mc_stats;
 
 /* ---- reference drop-ins ------------------------------------------------------------------- */
@@ -108,6 +113,14 @@ int ldpc_b200_mc_run(ldpc_b200_graph *g, const double *eps, int npoints, uint64_
 int ldpc_b200_mc_launch(ldpc_b200_graph *g, const double *eps, int npoints, uint64_t seed,
                         uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
                         uint64_t *d_counters, void *stream);
+/* The same launch for the erasure points [first_point, first_point + npoints) of a longer list: point p of this
+ * call is keyed as first_point + p by the channel generator, so a run can be split by POINT across GPUs or calls
+ * ((point, block) partitioning; the reference runs one OS process per point and merges the CSVs with
+ * tools/combine_data.py:64-95) and still decodes exactly the frames of the unsplit run.  d_counters holds the rows of
+ * THESE points. */
+int ldpc_b200_mc_launch_points(ldpc_b200_graph *g, const double *eps, int npoints, uint32_t first_point, uint64_t seed,
+                               uint64_t first_frame, uint64_t num_frames, int iterations, int expurgation,
+                               uint64_t *d_counters, void *stream);
 /* statistics of the launches since the last call (call after synchronising the stream) */
 int ldpc_b200_mc_stats_read(ldpc_b200_graph *g, ldpc_b200_mc_stats *stats);
 /* device durations (ms, CUDA events on the launch stream) of the decode kernels launched since the

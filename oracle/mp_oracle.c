@@ -20,6 +20,7 @@
  *   (c) when oracle/_ref exists, live differential runs against the compiled reference.
  */
 #include "mc_harness.h"
+#include "graph_twin.h"
 
 /*
  * Same signature and semantics as message_passing.c:7.
@@ -99,3 +100,7 @@ uint32_t orc_bec_word_export(uint64_t seed, uint32_t point, uint64_t q, uint32_t
 }
 
 void orc_philox_export(uint32_t *ctr4, uint32_t k0, uint32_t k1) { orc_philox4x32_10(ctr4, k0, k1); }
+
+int orc_generate_graph(int n, int dv, int dc, uint64_t seed, int *variable_lookup, int *check_lookup) {
+    return orc_generate_graph_twin(n, dv, dc, seed, variable_lookup, check_lookup);
+}

@@ -119,6 +119,32 @@ def reference() -> _Lib:
     return _cache["ref"]
 
 
+def reference_o3() -> _Lib:
+    """The same unmodified reference source compiled -O3 -march=x86-64-v3 (SURVEY 8d's second C-only row)."""
+    if "ref_o3" not in _cache:
+        path = os.path.join(HERE, "_ref", "libref_harness_o3.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref/libref_harness_o3.so not built (run `make -C oracle ref`)")
+        _cache["ref_o3"] = _Lib(ct.CDLL(path), "ref")
+    return _cache["ref_o3"]
+
+
+def have_ref_o3() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_harness_o3.so"))
+
+
+def generate_graph(n, dv, dc, seed=1):
+    """Oracle-side twin of the product's seeded generator (mode 1): (variable_lookup [n][dv], check_lookup [m][dc])."""
+    lib = restatement().lib
+    lib.orc_generate_graph.restype = ct.c_int
+    lib.orc_generate_graph.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_uint64, _P_I32, _P_I32]
+    vl = np.zeros(n * dv, dtype=np.int32)
+    cl = np.zeros(n * dv, dtype=np.int32)
+    if lib.orc_generate_graph(n, dv, dc, seed, _p(vl, _P_I32), _p(cl, _P_I32)) != 1:
+        raise RuntimeError("oracle graph twin failed")
+    return vl.reshape(n, dv), cl.reshape(n * dv // dc, dc)
+
+
 def best() -> _Lib:
     """The strongest checker available: compiled reference if present, else the restatement."""
     return reference() if have_ref() else restatement()

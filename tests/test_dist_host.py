@@ -26,6 +26,30 @@ def test_shard_frames_partitions_exactly():
         shard_frames(10, 0, 2, first_frame=5)
 
 
+def test_shard_items_covers_every_point_and_frame_once():
+    """(point, block) partitioning: every (point, frame) belongs to exactly one rank, blocks 128-aligned."""
+    from iib_project_ldpc_codes_b200.dist import shard_items
+    for npoints in (1, 2, 6, 20):
+        for total in (1, 127, 1000, 12345, 10 ** 7):
+            for world in (1, 2, 3, 4, 8):
+                cover = {p: [] for p in range(npoints)}
+                counts = []
+                for r in range(world):
+                    items = shard_items(npoints, total, r, world, first_frame=384)
+                    counts.append(sum(c for _, _, c in items))
+                    for p, lo, cnt in items:
+                        assert lo % 128 == 0 and cnt > 0
+                        cover[p].append((lo, cnt))
+                for p, segs in cover.items():
+                    pos = 384
+                    for lo, cnt in sorted(segs):
+                        assert lo == pos
+                        pos += cnt
+                    assert pos == 384 + total
+                if total >= 10 ** 7:
+                    assert max(counts) - min(counts) <= 128 * npoints + total // 4   # dealt evenly up to one block
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

@@ -280,6 +280,24 @@ def test_sharded_equals_whole(L, g1000):
         assert np.array_equal(acc, whole)
 
 
+def test_point_block_partitioning_equals_whole(L, g1000):
+    """(point, block) items (dist.shard_items) launched one erasure point at a time through
+    ldpc_b200_mc_launch_points: the channel generator keys every point by its index in the FULL list, so the summed
+    blocks equal the unsplit run bit for bit -- also through the staged pipeline and with expurgation."""
+    import torch
+    from iib_project_ldpc_codes_b200.dist import shard_items
+    eps, its, seed = [0.36, 0.40, 0.43], 200, 77
+    for total, exp in ((5000, -1), (20000, -1), (20000, 0)):
+        whole = g1000.mc_run(eps, seed, total, its, expurgation=exp, first_frame=256)
+        for world in (2, 8):
+            d = torch.zeros((len(eps), its + 6), dtype=torch.int64, device="cuda")
+            for r in range(world):
+                for p, lo, cnt in shard_items(len(eps), total, r, world, first_frame=256):
+                    g1000.mc_launch_point(eps[p], p, seed, cnt, its, d[p].data_ptr(), expurgation=exp, first_frame=lo)
+            torch.cuda.synchronize()
+            assert np.array_equal(d.cpu().numpy().view(np.uint64), whole), (total, exp, world)
+
+
 def test_full_size_properties_c2(L):
     """BASELINE config 2 at a larger frame count: size-independent invariants of the counter block."""
     vl, cl = L.generate_graph(10000, 3, 6, seed=1, mode=1)

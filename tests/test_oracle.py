@@ -87,3 +87,26 @@ def test_live_differential_against_compiled_reference(oracle):
             a = oracle.reference().mc_run(vl, cl, n, k, dv, dc, [0.38, 0.44], 5, 128, 200, 60, exp, nthreads=4)
             b = oracle.restatement().mc_run(vl, cl, n, k, dv, dc, [0.38, 0.44], 5, 128, 200, 60, exp, nthreads=2)
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,dv,dc,seed", [(24, 3, 6, 1), (1000, 3, 6, 1), (2000, 4, 8, 7), (60, 3, 4, 3), (10000, 3, 6, 1)])
+def test_oracle_graph_twin_equals_product_generator(oracle, n, dv, dc, seed):
+    """oracle/graph_twin.h lets the CPU reference arm of bench.py build the benchmark graph without loading the product
+    library; it must be the same graph."""
+    import iib_project_ldpc_codes_b200 as L
+    vo, co = oracle.generate_graph(n, dv, dc, seed)
+    vp, cp = L.generate_graph(n, dv, dc, seed=seed, mode=1)
+    assert np.array_equal(vo, vp) and np.array_equal(co, cp)
+
+
+def test_as_shipped_loop_restatement_runs_the_reference_object(oracle):
+    """oracle/as_shipped.py (the reference's Python frame loop around the unmodified .so) decodes like the C harness:
+    below threshold at n=240 most frames succeed, above none does."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    from oracle import as_shipped as A
+    vl, cl = oracle.generate_graph(240, 3, 6, 2)
+    frames, sec, blk = A.run_fixed_loop(240, 3, 6, 0.30, 50, cl, vl, seconds=30.0, max_frames=60)
+    assert frames == 60 and blk <= 6
+    frames, sec, blk = A.run_fixed_loop(240, 3, 6, 0.55, 50, cl, vl, seconds=30.0, max_frames=20)
+    assert frames == 20 and blk == 20
