@@ -32,10 +32,11 @@ class McStats(ct.Structure):
                 ("engine", ct.c_int32), ("words", ct.c_int32), ("teams", ct.c_int32), ("team_warps", ct.c_int32),
                 ("grid", ct.c_int32), ("smem_bytes", ct.c_int32), ("stages", ct.c_int32), ("kernel_launches", ct.c_int32),
                 ("spilled_records", ct.c_uint64), ("recounted_frames", ct.c_uint64), ("record_bytes", ct.c_int32),
-                ("tmem_lists", ct.c_int32)]
+                ("tmem_lists", ct.c_int32),
+                ("overlap_producers", ct.c_int32), ("reserved_", ct.c_int32), ("overlap_cycles", ct.c_uint64 * 4)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "overlap_cycles" else int(getattr(self, k))) for k, _ in self._fields_}
 
 
 # every symbol include/ldpc_b200.h declares (tests check the shared object exports all of them)

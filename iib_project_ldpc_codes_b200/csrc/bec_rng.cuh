@@ -33,6 +33,24 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
     }
 }
 
+// The same rounds with the 20 round keys READ from `rk` (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85 for r = 0..9, made on
+// the host: philox_round_keys).  When `rk` is a kernel parameter the keys are constant-bank operands of the LOP3s
+// and occupy no registers, which lets the scheduler interleave more independent chains.
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                 const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+}
+__host__ __device__ inline void philox_round_keys(uint32_t seed_lo, uint32_t seed_hi, uint32_t (&rk)[20]) {
+    for (int r = 0; r < 10; r++) { rk[2 * r] = seed_lo + (uint32_t)r * 0x9E3779B9u; rk[2 * r + 1] = seed_hi + (uint32_t)r * 0xBB67AE85u; }
+}
+
 struct BecParams {
     uint32_t seed_lo, seed_hi;
     uint32_t threshold;  // low 32 bits of T
@@ -101,6 +119,20 @@ __device__ __forceinline__ void bec_block(const BecParams& bp, uint32_t point, u
     }
 }
 
+__device__ __forceinline__ void bec_block_rk(const BecParams& bp, const uint32_t (&rk)[20], uint32_t point, uint64_t q,
+                                             uint32_t var, int b, uint32_t& lt, uint32_t& eq) {
+    uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
+    philox4x32_10_rk(r0, r1, r2, r3, rk);
+    const uint32_t r[4] = {r0, r1, r2, r3};
+    const uint32_t tb = bp.threshold << (4 * b);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const uint32_t m = (uint32_t)((int32_t)(tb << s) >> 31);
+        lt |= eq & ~r[s] & m;
+        eq &= ~(r[s] ^ m);
+    }
+}
+
 // true when block b was the last one bec_word would have executed for this word
 __device__ __forceinline__ bool bec_done_after(const BecParams& bp, int b, uint32_t eq) {
     return eq == 0u || b == 7 || (bp.threshold << (4 * b + 4)) == 0u;
@@ -124,6 +156,24 @@ __device__ __forceinline__ void bec_first8(const BecParams& bp, const BecMasks8&
     for (int b = 0; b < 2; b++) {
         uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
         philox4x32_10(r0, r1, r2, r3, bp.seed_lo, bp.seed_hi);
+        const uint32_t r[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t m = M.m[4 * b + s];
+            lt |= eq & ~r[s] & m;
+            eq &= ~(r[s] ^ m);
+        }
+    }
+}
+
+// bec_first8 with host-made round keys
+__device__ __forceinline__ void bec_first8_rk(const BecMasks8& M, const uint32_t (&rk)[20], uint32_t point, uint64_t q,
+                                              uint32_t var, uint32_t& lt, uint32_t& eq) {
+    lt = 0u; eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        uint32_t r0 = var, r1 = (uint32_t)q, r2 = (uint32_t)(q >> 32), r3 = (point << 8) | (uint32_t)b;
+        philox4x32_10_rk(r0, r1, r2, r3, rk);
         const uint32_t r[4] = {r0, r1, r2, r3};
 #pragma unroll
         for (int s = 0; s < 4; s++) {

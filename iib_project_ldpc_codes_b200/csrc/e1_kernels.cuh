@@ -95,6 +95,10 @@ struct E1Params {
     int tm;                                 // 1: on (kernels instantiated with TM = true)
     int tm_cpw, tm_trips_c, tm_trips_v;     // columns per warp, check / variable trips per thread
     int tm_full_c, tm_full_v;               // trips in which every thread of a team has a node (m / T, n / T)
+    // overlapped stage 0 (e1_overlap.cuh): warps [0, team_warps) decode, warps [team_warps, team_warps + ov_np) draw the
+    // next group's erasure pattern into a staging buffer meanwhile
+    int ov_np;                              // producer (channel) warps; 0 = not the overlapped kernel
+    uint32_t sm_stage, sm_q, sm_pscr, sm_mbox, ov_qentries;   // staging pattern | draw queue | producer scratch | mailbox
     // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
     // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
     // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c
@@ -114,6 +118,7 @@ struct E1Params {
     uint32_t k16, k16s, vec_bytes;
     uint32_t draw_qcap;   // test hook: cap on the continuation queue of team_draw (0 = as large as `two` allows)
     uint32_t seed_lo, seed_hi;   // run seed (same in every bec[p]); a kernel parameter so the Philox round keys are uniform
+    uint32_t rk[20];             // the 20 Philox round keys of that seed (philox_round_keys): constant-bank operands
     int npoints, cap, expurgation;
     uint32_t point0;                    // erasure point p of this launch is keyed as point0 + p by the channel generator
     unsigned long long first_word;      // word index q of the first frame (first_frame / 32)
@@ -594,11 +599,19 @@ __device__ __noinline__ uint32_t bec_finish(const BecParams& bp, uint32_t point,
 // levels, no exit tests); the ~12 % of words that still have an undecided frame are appended to a queue
 // (in the `two` array, idle during the draw) and continued one block per round by whichever thread picks
 // them up: 2.15 blocks per word.  Thread-local partial results: `red` (OR per word) and `cnt` (popcount).
-template <int WORDS, bool MASKED>
-__device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
+// what team_draw reads of the kernel parameters (E1Params has the same members; the producer warps of the overlapped
+// stage-0 kernel, e1_overlap.cuh, pass this small copy)
+struct DrawParams {
+    int n, m;
+    const uint16_t* var_orig;
+    uint32_t seed_lo, seed_hi, draw_qcap;
+};
+
+template <int WORDS, bool MASKED, class PT = E1Params>
+__device__ __forceinline__ void team_draw(const PT& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
                                           unsigned long long q0, const uint32_t (&valid)[WORDS],
                                           const uint32_t (&mask)[WORDS], VecT<WORDS>* x, uint32_t* qbuf,
-                                          uint32_t* qc, uint32_t (&red)[WORDS], uint32_t& cnt) {
+                                          uint32_t* qc, uint32_t (&red)[WORDS], uint32_t& cnt, uint32_t qentries = 0) {
     LDPC_FORW red[w] = 0u;
     cnt = 0u;
     BecParams bp = bp_;
@@ -617,32 +630,48 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
     }
     uint32_t* xs = reinterpret_cast<uint32_t*>(x);
     uint2* q2 = reinterpret_cast<uint2*>(qbuf);
-    uint32_t entries = (uint32_t)P.m * WORDS / 2u;
+    // qentries != 0: the queue is a dedicated buffer of that many 8-byte entries (the overlapped stage-0 kernel,
+    // e1_overlap.cuh, draws while `two` is in use); the variables are then drawn in slices small enough that the
+    // expected 12 % of unfinished words (margin: 1/6) fit the first queue
+    uint32_t entries = qentries ? qentries : (uint32_t)P.m * WORDS / 2u;
     if (P.draw_qcap && P.draw_qcap < entries) entries = P.draw_qcap;   // overflowing words finish in-thread (bec_finish)
     const uint32_t capB = entries / 8u, capA = entries - capB;
     uint2* const qA = q2;
     uint2* const qB = q2 + capA;
-    if (t.tid < 8) qc[t.tid] = 0u;
-    team_sync(t);
+    int slice = P.n;
+    if (qentries) slice = max(t.nthr, (int)(capA * 6u / WORDS) / t.nthr * t.nthr);
     const BecMasks8 M = bec_masks8(bp);
     const bool deeper = (bp.threshold << 8) != 0u;
-    for (int i = t.tid; i < P.n; i += t.nthr) {
+    for (int s0 = 0; s0 < P.n; s0 += slice) {
+    const int s1 = min(P.n, s0 + slice);
+    if (t.tid < 8) qc[t.tid] = 0u;
+    team_sync(t);
+    // the original id of the NEXT variable is fetched (L2) one trip ahead, and the Philox chains of all the words of a
+    // variable run side by side before any queue traffic: with few warps drawing (the producer warps of
+    // e1_overlap.cuh) the loop is bound by latency, not by issue slots
+    uint32_t var = 0u;
+    if (s0 + t.tid < s1) var = P.var_orig ? (uint32_t)P.var_orig[s0 + t.tid] : (uint32_t)(s0 + t.tid);
+    for (int i = s0 + t.tid; i < s1; i += t.nthr) {
         VecT<WORDS> xi;
-        const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : (uint32_t)i;
+        uint32_t var_next = 0u;
+        if (i + t.nthr < s1) var_next = P.var_orig ? (uint32_t)P.var_orig[i + t.nthr] : (uint32_t)(i + t.nthr);
+        uint32_t lt[WORDS], eq[WORDS];
         LDPC_FORW {
-            uint32_t lt, eq;
-            bec_first8(bp, M, point, q0 + w, var, lt, eq);
-            eq &= valid[w];
-            if (eq != 0u && deeper) {
+            bec_first8(bp, M, point, q0 + w, var, lt[w], eq[w]);
+            eq[w] &= valid[w];
+        }
+        LDPC_FORW {
+            if (eq[w] != 0u && deeper) {
                 const uint32_t slot = atomicAdd(&qc[1], 1u);
-                if (slot < capA) qA[slot] = make_uint2((uint32_t)i * WORDS + w, eq);
-                else lt |= bec_finish(bp, point, q0 + w, var, 2, eq);
+                if (slot < capA) qA[slot] = make_uint2((uint32_t)i * WORDS + w, eq[w]);
+                else lt[w] |= bec_finish(bp, point, q0 + w, var, 2, eq[w]);
             }
-            xi.a[w] = lt & valid[w];
+            xi.a[w] = lt[w] & valid[w];
             red[w] |= xi.a[w];
             cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
         }
         x[i] = xi;
+        var = var_next;
     }
     team_sync(t);
     for (int b = 2; b < 8; b++) {
@@ -675,6 +704,7 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
         }
         team_sync(t);
     }
+    }   // slices
 }
 
 // stage the resident part of the variable-side lists (v2c_global): every packed array keeps its nodes [0, v2c_res)

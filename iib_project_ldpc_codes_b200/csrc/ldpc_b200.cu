@@ -22,6 +22,7 @@
 #include "relabel.hpp"
 #include "e2_kernels.cuh"
 #include "e1_staged.cuh"
+#include "e1_overlap.cuh"
 
 using namespace ldpc;
 
@@ -75,6 +76,8 @@ struct E1Config {
     uint32_t sm_c2v, sm_v2c, sm_team0, sm_team_stride, sm_x, sm_t, sm_v, sm_p, sm_hbuf, sm_scr;
     int v2c_res = 0; uint32_t sm_vres = 0;   // v2c_global: resident part of the variable-side lists
     bool tm = false; int tm_cpw = 0, tm_trips_c = 0, tm_trips_v = 0;   // socket lists in tensor memory (e1_tmem.cuh)
+    // overlapped stage 0 (e1_overlap.cuh): team_warps consumer warps + ov_np producer warps
+    int ov_np = 0; uint32_t sm_stage = 0, sm_q = 0, sm_pscr = 0, sm_mbox = 0, ov_qentries = 0;
 };
 
 struct StagePlan {
@@ -119,7 +122,7 @@ struct ldpc_b200_graph {
     int engine = 0;  // 0 auto, 1 force E1, 2 force E2
     // staged E1 Monte-Carlo: cut points per (eps list, cap, words), spill buffers, per-stage record counts
     std::unordered_map<uint64_t, StagePlan> plans;
-    void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0;
+    void* d_spill[2] = {nullptr, nullptr}; size_t spill_bytes = 0; int spill_budget_mb = 0;
     uint32_t* d_idlist = nullptr; size_t idlist_bytes = 0;   // expurgated runs: frames listed for the re-count pass
     unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
     // batched decode buffers (cached between calls)
@@ -139,7 +142,8 @@ struct ldpc_b200_graph {
     // tuning overrides
     int tune_words = 0, tune_teams = 0, tune_team_warps = 0;
     // statistics of launches since last read
-    unsigned long long* d_stats = nullptr;  // [4]: phys frame-iterations, second-pass groups, spilled records, re-counted frames
+    unsigned long long* d_stats = nullptr;  // [8]: phys frame-iterations, second-pass groups, spilled records, re-counted frames,
+                                            //      overlapped stage 0: consumer wait / producer wait / draw / consumer busy cycles (thread 0 of SM-resident CTAs)
     ldpc_b200_mc_stats last = {};
     // kernel timing ring
     static constexpr int RING = 256;
@@ -200,6 +204,52 @@ static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg) {
         return true;
     }
     return false;
+}
+
+// Plan of the overlapped stage-0 kernel (e1_overlap.cuh) for the word width the staged plan `base` chose: ONE consumer
+// team + producer warps, the state plus a staging pattern, the producers' draw queue and scratch in shared memory.
+// Used when one team owns the SM anyway (large graphs: nothing else would overlap the ALU-only channel draw with the
+// shared-memory-bound decoding).  LDPC_B200_OVERLAP: 0 auto, 1 force where it fits, 2 off; LDPC_B200_PRODUCERS = warps.
+static bool plan_e1_overlap(const ldpc_b200_graph* g, int cap, const E1Config& base, E1Config& out) {
+    const int mode = tuning_env("LDPC_B200_OVERLAP");
+    if (mode == 2 || !base.tm) return false;
+    if (mode != 1 && base.teams != 1) return false;
+    const int words = base.words;
+    const int max_warps = e1_threads(words) / 32;
+    int np = tuning_env("LDPC_B200_PRODUCERS");
+    if (np <= 0) np = 8;   // measured at n = 10^4 (profiles/r2b_overlap_sweep.log): 2: 5.5, 4: 7.0, 6: 7.8, 8: 8.1 e7 frames/s (off: 7.1)
+    if (np >= max_warps) return false;
+    const uint32_t limit = (uint32_t)g->smem_optin - 64;
+    E1Config c;
+    uint32_t off = 0;
+    c.sm_x = off; off += align_up((uint32_t)g->n * 4 * words, 16);
+    c.sm_t = off; off += align_up((uint32_t)g->m * 4 * words, 16);
+    c.sm_v = off; c.sm_p = off;
+    c.sm_hbuf = off; off += align_up((uint32_t)(cap + 1) * 4, 16);
+    c.sm_scr = off; off += align_up((uint32_t)e1_scr_words(words) * 4, 16);
+    c.sm_stage = off; off += align_up((uint32_t)g->n * 4 * words, 16);
+    c.sm_pscr = off; off += align_up((uint32_t)e1_scr_words(words) * 4, 16);
+    c.sm_mbox = off; off += 64;
+    c.sm_q = off; off += (uint32_t)np * ov_wq_bytes();   // one private draw queue per producer warp
+    c.ov_qentries = OV_WQ;
+    if (off > limit) return false;
+    // consumer warps: as many as the thread budget and the tensor-memory columns allow
+    int nc = 0;
+    for (int tw = max_warps - np; tw >= 1; tw--) {
+        const int nthr = tw * 32, wpq = (tw + 3) / 4;
+        const int tc = (g->m + nthr - 1) / nthr, tv = (g->n + nthr - 1) / nthr;
+        if ((tc * g->dc + tv * g->dv) * wpq > 512) continue;
+        nc = tw; break;
+    }
+    if (nc < 4) return false;
+    const int nthr = nc * 32;
+    c.words = words; c.teams = 1; c.team_warps = nc; c.values = false; c.v2c_global = false;
+    c.sm_c2v = 0; c.sm_v2c = 0; c.sm_team0 = 0; c.sm_team_stride = off; c.smem = off;
+    c.tm = true; c.tm_trips_c = (g->m + nthr - 1) / nthr; c.tm_trips_v = (g->n + nthr - 1) / nthr;
+    c.tm_cpw = c.tm_trips_c * g->dc + c.tm_trips_v * g->dv;
+    c.ov_np = np;
+    out = c;
+    return true;
 }
 
 // Shared-memory plan for E1.  Returns false if even one W=32 team does not fit.
@@ -275,17 +325,24 @@ static bool plan_e1(const ldpc_b200_graph* g, int cap, bool values, bool decode,
     return false;
 }
 
+// geometry of a plan (threads, shared-memory map, tensor-memory map) -> kernel parameters; leaves the run fields alone
+static void set_geometry(const ldpc_b200_graph* g, const E1Config& c, E1Params& P) {
+    P.vec_bytes = 4u * (uint32_t)c.words; P.k16 = 65536u; P.k16s = 65536u * P.vec_bytes;
+    P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0; P.v2c_res = c.v2c_res; P.sm_vres = c.sm_vres;
+    P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
+    P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
+    P.tm = c.tm ? 1 : 0; P.tm_cpw = c.tm_cpw; P.tm_trips_c = c.tm_trips_c; P.tm_trips_v = c.tm_trips_v;
+    P.tm_full_c = g->m / (c.team_warps * 32); P.tm_full_v = g->n / (c.team_warps * 32);
+    P.ov_np = c.ov_np; P.sm_stage = c.sm_stage; P.sm_q = c.sm_q; P.sm_pscr = c.sm_pscr; P.sm_mbox = c.sm_mbox; P.ov_qentries = c.ov_qentries;
+}
+
 static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1Params& P) {
     memset(&P, 0, sizeof P);
     P.c2v = g->d_c2v16; P.v2c = g->d_v2c16;
     P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.n_pad = g->n_pad; P.m_pad = g->m_pad;
-    P.draw_qcap = (uint32_t)std::max(0, tuning_env("LDPC_B200_DRAW_QCAP")); P.k16 = 65536u; P.vec_bytes = 4u * (uint32_t)c.words; P.k16s = 65536u * P.vec_bytes;
-    P.team_warps = c.team_warps; P.teams = c.teams; P.v2c_global = c.v2c_global ? 1 : 0; P.v2c_res = c.v2c_res; P.sm_vres = c.sm_vres;
-    P.sm_c2v = c.sm_c2v; P.sm_v2c = c.sm_v2c; P.sm_team0 = c.sm_team0; P.sm_team_stride = c.sm_team_stride;
-    P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
+    P.draw_qcap = (uint32_t)std::max(0, tuning_env("LDPC_B200_DRAW_QCAP"));
+    set_geometry(g, c, P);
     P.cap = cap;
-    P.tm = c.tm ? 1 : 0; P.tm_cpw = c.tm_cpw; P.tm_trips_c = c.tm_trips_c; P.tm_trips_v = c.tm_trips_v;
-    P.tm_full_c = g->m / (c.team_warps * 32); P.tm_full_v = g->n / (c.team_warps * 32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,8 +396,8 @@ static int ldpc_b200_graph_create_impl(const int* v2c, const int* c2v, int n, in
     }
     {
         cudaError_t e = cudaMalloc(&g->d_work, sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMalloc(&g->d_stats, 4 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&g->d_stats, 8 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, 8 * sizeof(unsigned long long));
         if (e != cudaSuccess) { ldpc_b200_graph_destroy(g); return fail(LDPC_B200_ECUDA, "graph_create: %s", cudaGetErrorString(e)); }
     }
     *out = g;
@@ -621,6 +678,7 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
     P.c2v = g->placed[cfg.words].d_c2v; P.v2c = g->placed[cfg.words].d_v2c; P.var_orig = g->placed[cfg.words].d_var_orig;
     const unsigned long long W = 32ull * cfg.words;
     P.bec = g->d_bec; P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.npoints = npoints; P.expurgation = expurgation;
+    philox_round_keys(P.seed_lo, P.seed_hi, P.rk);
     P.point0 = first_point;
     P.first_word = first_frame / 32; P.num_frames = num_frames;
     P.groups_per_point = (num_frames + W - 1) / W;
@@ -651,6 +709,7 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
     const int slot = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
     if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));
     int grid_used = grid;
+    g->last.overlap_producers = 0;
     if (plan) {
         rc = e1_mc_staged(g, cfg, P, *plan, npoints, first_frame, num_frames, two_pass, expurgation, st, &grid_used);
         if (rc) return rc;
@@ -696,10 +755,11 @@ extern "C" int ldpc_b200_mc_launch_points(ldpc_b200_graph* g, const double* eps,
 extern "C" int ldpc_b200_mc_stats_read(ldpc_b200_graph* g, ldpc_b200_mc_stats* stats) {
     if (!g || !stats) return fail(LDPC_B200_EINVAL, "mc_stats_read: NULL argument");
     CUDA_TRY(cudaSetDevice(g->device));
-    unsigned long long h[4];
+    unsigned long long h[8];
     CUDA_TRY(cudaMemcpy(h, g->d_stats, sizeof h, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemset(g->d_stats, 0, sizeof h));
     *stats = g->last;
+    for (int i = 0; i < 4; i++) stats->overlap_cycles[i] = h[4 + i];
     stats->phys_frame_iterations = h[0];
     stats->second_pass_groups = h[1];
     stats->spilled_records = h[2];

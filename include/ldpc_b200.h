@@ -50,6 +50,10 @@ typedef struct ldpc_b200_mc_stats {
     uint64_t recounted_frames;      /* expurgated runs: frames listed by pass 1 and re-drawn by the re-count pass  */
     int32_t record_bytes;           /* bytes per spill record: DRAM traffic = spilled_records * record_bytes * 2   */
     int32_t tmem_lists;             /* 1 = socket lists in tensor memory (tcgen05.ld-supplied gather addresses)    */
+    int32_t overlap_producers;      /* > 0: stage 0 ran as the producer/consumer kernel with this many channel-draw warps */
+    int32_t reserved_;
+    uint64_t overlap_cycles[4];     /* overlapped stage 0, SM cycles summed over CTAs: consumers waiting for a pattern,
+                                       producers waiting for the staging buffer, producers drawing, consumers decoding */
 } ldpc_b200_mc_stats;
 
 /* ---- reference drop-ins ------------------------------------------------------------------- */

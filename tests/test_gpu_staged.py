@@ -177,3 +177,89 @@ def test_expurgated_two_pass_other_code_and_chunks(L, oracle):
     hi = oracle.best().mc_run(vl, cl, 2000, 1000, 4, 8, [0.40], seed, 0, 9000, its, 0, nthreads=16)
     got_hi, st_hi = g.mc_run([0.40], seed, 9000, its, expurgation=0, return_stats=True)
     assert np.array_equal(got_hi, hi) and st_hi["stages"] == 1
+
+
+def _env(**kv):
+    class _E:
+        def __enter__(self):
+            self.old = {k: os.environ.get(k) for k in kv}
+            for k, v in kv.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = str(v)
+
+        def __exit__(self, *a):
+            for k, v in self.old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return _E()
+
+
+@pytest.mark.parametrize("words,producers", [(4, 4), (2, 2), (2, 8), (1, 1)])
+def test_overlapped_stage0_equals_reference_n1000(L, oracle, words, producers):
+    """Producer / consumer stage 0 (e1_overlap.cuh), forced on a small graph: same counters as the reference loop,
+    for several producer counts, ragged frame counts, eps incl. 0 and 1."""
+    vl, cl = L.generate_graph(1000, 3, 6, seed=1, mode=1)
+    eps, seed, frames, its = [0.40, 0.0, 0.43, 1.0], 99, 24000 + 45, 200
+    want = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed, 128, frames, its, -1, nthreads=16)
+    with _env(LDPC_B200_OVERLAP=1, LDPC_B200_PRODUCERS=producers, LDPC_B200_FORCE_CUTS="6,20"):
+        g = L.Graph(vl, cl)
+        g.set_tuning(words, 0, 0)
+        got, st = g.mc_run(eps, seed, frames, its, first_frame=128, return_stats=True)
+    assert st["overlap_producers"] == producers and st["words"] == words, st
+    assert np.array_equal(got, want)
+    with _env(LDPC_B200_OVERLAP=2):
+        g = L.Graph(vl, cl)
+        g.set_tuning(words, 0, 0)
+        got2, st2 = g.mc_run(eps, seed, frames, its, first_frame=128, return_stats=True)
+    assert st2["overlap_producers"] == 0
+    assert np.array_equal(got2, want)
+
+
+def test_overlapped_stage0_small_queue_and_expurgated(L, oracle):
+    """a draw queue that overflows (words finish in-thread) and the expurgated two-pass run through the overlapped kernel"""
+    vl, cl = L.generate_graph(2000, 4, 8, seed=3, mode=1)
+    eps, seed, frames, its = [0.34, 0.37], 8, 20000, 120
+    for exp in (-1, 0, 3):
+        want = oracle.best().mc_run(vl, cl, 2000, 1000, 4, 8, eps, seed, 0, frames, its, exp, nthreads=16)
+        with _env(LDPC_B200_OVERLAP=1, LDPC_B200_DRAW_QCAP=64, LDPC_B200_EXP2PASS=1, LDPC_B200_FORCE_CUTS="5,17"):
+            g = L.Graph(vl, cl)
+            got, st = g.mc_run(eps, seed, frames, its, expurgation=exp, return_stats=True)
+        assert st["overlap_producers"] > 0, st
+        assert np.array_equal(got, want), f"expurgation={exp}"
+
+
+def test_overlapped_stage0_is_default_at_c2_size(L):
+    """n = 10^4 (one team owns the SM): the overlapped kernel is the default and equals the plain staged kernel"""
+    vl, cl = L.generate_graph(10000, 3, 6, seed=1, mode=1)
+    eps, seed, frames, its = [0.40, 0.43], 5, 100000, 200
+    g1 = L.Graph(vl, cl)
+    a, sa = g1.mc_run(eps, seed, frames, its, return_stats=True)
+    with _env(LDPC_B200_OVERLAP=2):
+        g2 = L.Graph(vl, cl)
+        b, sb = g2.mc_run(eps, seed, frames, its, return_stats=True)
+    assert sa["overlap_producers"] > 0 and sb["overlap_producers"] == 0
+    assert np.array_equal(a, b)
+
+
+def test_spill_budget_follows_free_memory_and_fails_cleanly(L, oracle):
+    """The spill buffers take at most a fifth of the free device memory (LDPC_B200_FAKE_FREE_MB pretends there is
+    little): small chunks, same counters.  A budget that cannot be allocated is a clean error, and the handle still
+    works afterwards."""
+    vl, cl = L.generate_graph(1000, 3, 6, seed=1, mode=1)
+    eps, seed, frames, its = [0.40, 0.42], 77, 30000, 200
+    want = oracle.best().mc_run(vl, cl, 1000, 500, 3, 6, eps, seed, 0, frames, its, -1, nthreads=16)
+    with _env(LDPC_B200_FAKE_FREE_MB=5):      # 1 MB per buffer: 4096 frames per point and chunk
+        g = L.Graph(vl, cl)
+        got, st = g.mc_run(eps, seed, frames, its, return_stats=True)
+    assert st["stages"] > 1 and np.array_equal(got, want)
+    with _env(LDPC_B200_SPILL_MB=100000000):  # no cap: 40 points x 2^25 frames x 128 B = 172 GB per buffer
+        g = L.Graph(vl, cl)
+        with pytest.raises(L.LdpcB200Error) as ei:
+            g.mc_run([0.30 + 0.001 * i for i in range(40)], seed, 1 << 34, its)
+        assert "spill" in str(ei.value)
+    got2 = g.mc_run(eps, seed, frames, its)
+    assert np.array_equal(got2, want)

@@ -37,6 +37,9 @@ for cfg in cfgs:
         print(f"cfg={cfg} words={s['words']} teams={s['teams']} tw={s['team_warps']} grid={s['grid']} smem={s['smem_bytes']} "
               f"ms={ms:.2f} frames/s={fr/ms*1e3:.4g} EU/s={ex*n*dv/ms*1e3:.4g} it/frame={ex/fr:.2f} "
               f"inflation={s['phys_frame_iterations']/ex:.3f} engine={s['engine']} stages={s['stages']} launches={s['kernel_launches']} "
-              f"place={g.placement_info(s['words']) if s['engine'] == 1 else None}", flush=True)
+              f"place={g.placement_info(s['words']) if s['engine'] == 1 else None}"
+              + (f" overlap: producers={s['overlap_producers']} Mcycles/CTA cons_wait={s['overlap_cycles'][0]/s['grid']/1e6:.2f} "
+                 f"prod_wait={s['overlap_cycles'][1]/s['grid']/1e6:.2f} draw={s['overlap_cycles'][2]/s['grid']/1e6:.2f} "
+                 f"decode={s['overlap_cycles'][3]/s['grid']/1e6:.2f}" if s.get('overlap_producers') else ""), flush=True)
     except Exception as e:  # noqa: BLE001
         print(f"cfg={cfg} failed: {e}", flush=True)
