@@ -215,7 +215,8 @@ static bool plan_e1_overlap(const ldpc_b200_graph* g, int cap, const E1Config& b
     if (mode == 2 || !base.tm) return false;
     if (mode != 1 && base.teams != 1) return false;
     const int words = base.words;
-    const int max_warps = e1_threads(words) / 32;
+    int max_warps = ov_threads(words) / 32;
+    if (tuning_env("LDPC_B200_OV_THREADS") >= 64) max_warps = std::min(max_warps, tuning_env("LDPC_B200_OV_THREADS") / 32);
     int np = tuning_env("LDPC_B200_PRODUCERS");
     if (np <= 0) np = 8;   // measured at n = 10^4 (profiles/r2b_overlap_sweep.log): 2: 5.5, 4: 7.0, 6: 7.8, 8: 8.1 e7 frames/s (off: 7.1)
     if (np >= max_warps) return false;
