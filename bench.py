@@ -150,6 +150,17 @@ def cpu_baseline(wl, vl, cl, fpp=None, with_variants=True, got_fn=None):
             out["as_shipped_python_loop"] = {"value": fr / sec, "unit": "frames/s", "cores": 1,
                                              "sample": f"{fr} frames at eps={eps[len(eps) // 2]} in {sec:.1f} s, numpy channel "
                                                        "+ ctypes marshalling + CDLL per frame as the reference does"}
+            # the SAME loop with the one-line swap of INTEGRATION.md: message_passing.so -> libldpc_b200.so (one GPU
+            # launch per frame through the 9-argument drop-in symbol)
+            try:
+                import iib_project_ldpc_codes_b200 as L
+                A.run_fixed_loop(n, dv, dc, eps[len(eps) // 2], cap, cl, vl, seconds=0.5, lib_path=L.LIB_PATH)   # warm the handle cache
+                fr2, sec2, _ = A.run_fixed_loop(n, dv, dc, eps[len(eps) // 2], cap, cl, vl, seconds=3.0, lib_path=L.LIB_PATH)
+                out["drop_in_symbol_python_loop"] = {"value": fr2 / sec2, "unit": "frames/s", "cores": 1,
+                                                     "sample": f"{fr2} frames in {sec2:.1f} s: the reference's per-frame loop calling "
+                                                               "message_passing() of libldpc_b200.so (one frame per GPU launch)"}
+            except Exception as e:  # noqa: BLE001
+                out["drop_in_symbol_python_loop"] = {"error": str(e)}
     return out
 
 
@@ -257,8 +268,9 @@ def measure_fixed(E, name, wl, steps, warmup, with_cpu, cold=True):
             tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
         cold_frames = npoints * (frames if strong else frames * world)
         cold_info = {"value": cold_frames / float(tt.item()), "unit": "frames/s", "seconds": float(tt.item()),
-                     "what": "fresh handle: graph upload + placement search (or its disk cache) + pilot + ONE step through "
-                             "ldpc_b200_mc_run with host buffers"}
+                     "what": "fresh handle: graph upload + pilot + ONE step through ldpc_b200_mc_run with host buffers; the "
+                             "placement search runs on background host threads meanwhile (first chunks decode on the "
+                             "natural layout), LDPC_B200_CACHE=0 so that no cached placement is used"}
     else:
         g = L.Graph(vl, cl, device=local)
 
@@ -276,6 +288,8 @@ def measure_fixed(E, name, wl, steps, warmup, with_cpu, cold=True):
 
     for s in range(warmup):
         step(s)
+        if s == 0:
+            g.wait_placement()   # the placement search runs in the background of the first step; time the placed layout
     barrier()
     g.kernel_times_ms()
     g.mc_stats()
@@ -472,6 +486,7 @@ def _emit(line):
 
 def main():
     _quiet_stdout()
+    os.environ.setdefault("LDPC_B200_CACHE", "0")   # no placement read from (or left on) disk: the cold leg is really cold
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

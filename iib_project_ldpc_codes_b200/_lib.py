@@ -45,7 +45,7 @@ EXPORTS = [
     "ldpc_b200_generate_graph", "ldpc_b200_graph_create", "ldpc_b200_graph_destroy", "ldpc_b200_counters_len",
     "ldpc_b200_mc_run", "ldpc_b200_mc_launch", "ldpc_b200_mc_launch_points", "ldpc_b200_mc_stats_read", "ldpc_b200_kernel_times",
     "ldpc_b200_decode_batch", "ldpc_b200_draw_patterns", "ldpc_b200_set_tuning", "ldpc_b200_smem_probe",
-    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble", "ldpc_b200_generate_graph_indexed",
+    "ldpc_b200_set_place_effort", "ldpc_b200_placement_info", "ldpc_b200_placement_wait", "ldpc_b200_set_engine", "ldpc_b200_mc_run_ensemble", "ldpc_b200_generate_graph_indexed",
 ]
 
 _lib = None
@@ -105,6 +105,8 @@ def load() -> ct.CDLL:
     lib.ldpc_b200_smem_probe.argtypes = [ct.c_int, P_F64]
     lib.ldpc_b200_set_place_effort.restype = ct.c_int
     lib.ldpc_b200_set_place_effort.argtypes = [ct.c_void_p, ct.c_int]
+    lib.ldpc_b200_placement_wait.restype = ct.c_int
+    lib.ldpc_b200_placement_wait.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_int)]
     lib.ldpc_b200_placement_info.restype = ct.c_int
     lib.ldpc_b200_placement_info.argtypes = [ct.c_void_p, ct.c_int, P_F64, P_F64, P_F64]
     lib.ldpc_b200_set_engine.restype = ct.c_int

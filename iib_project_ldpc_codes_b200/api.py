@@ -131,6 +131,14 @@ class Graph:
     def set_place_effort(self, effort):
         check(self._lib.ldpc_b200_set_place_effort(self._h, effort))
 
+    def wait_placement(self, words=0):
+        """Blocks until the background placement searches of this handle are finished and uploaded (launches made
+        before that decode on the natural layout: same results, slower kernels).  Returns the source of the
+        placement for `words` words per node: 0 none, 1 searched in this process, 2 read from the disk cache."""
+        src = ct.c_int(0)
+        check(self._lib.ldpc_b200_placement_wait(self._h, int(words), ct.byref(src)))
+        return src.value
+
     def placement_info(self, words):
         a, b, c = ct.c_double(), ct.c_double(), ct.c_double()
         check(self._lib.ldpc_b200_placement_info(self._h, words, ct.byref(a), ct.byref(b), ct.byref(c)))

@@ -133,6 +133,8 @@ struct E1Params {
     const unsigned long long* rc_cnt;    // [npoints]
     unsigned long long rc_stride;
     // batched decode work (WORDS == 1)
+    const int8_t* mvc8;    // != NULL: ONE group (<= 32 frames) read from / written to int8 symbols [frames][n] in {0,1,2}
+                           // directly (the single-frame drop-in: no pack / unpack kernels, one launch per call)
     const uint32_t* xin;   // [groups][n] erasure plane
     const uint32_t* vin;   // [groups][n] value plane
     uint32_t* xout;
@@ -1074,12 +1076,26 @@ __global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_decode_kernel(const __gr
          gi += (unsigned long long)gridDim.x * P.teams) {
         const unsigned long long f0 = gi * 32ull;
         const uint32_t valid = P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u);
-        const uint32_t* gx = P.xin + (size_t)gi * P.n;
-        const uint32_t* gv = P.vin + (size_t)gi * P.n;
-        for (int i = t.tid; i < P.n; i += t.nthr) {
-            const uint32_t xi = gx[i] & valid;
-            x[i].a[0] = xi;
-            if (VALUES) val[i].a[0] = gv[i] & ~xi & valid;
+        if (P.mvc8) {
+            const int nf = (int)min((unsigned long long)32, P.num_frames - f0);
+            for (int i = t.tid; i < P.n; i += t.nthr) {
+                uint32_t xi = 0u, vi = 0u;
+                for (int b = 0; b < nf; b++) {
+                    const int8_t sym = P.mvc8[(size_t)(f0 + b) * P.n + i];
+                    xi |= (uint32_t)(sym == 2) << b;
+                    vi |= (uint32_t)(sym == 1) << b;
+                }
+                x[i].a[0] = xi;
+                if (VALUES) val[i].a[0] = vi;
+            }
+        } else {
+            const uint32_t* gx = P.xin + (size_t)gi * P.n;
+            const uint32_t* gv = P.vin + (size_t)gi * P.n;
+            for (int i = t.tid; i < P.n; i += t.nthr) {
+                const uint32_t xi = gx[i] & valid;
+                x[i].a[0] = xi;
+                if (VALUES) val[i].a[0] = gv[i] & ~xi & valid;
+            }
         }
         team_sync(t);
 
@@ -1116,9 +1132,18 @@ __global__ void __launch_bounds__(E1_MAX_THREADS, 1) e1_decode_kernel(const __gr
             for (int j = it; j < P.cap; j++) P.errors[frame * (unsigned long long)P.cap + j] = (int)my_count;
             P.ret[frame] = my_ret;
         }
-        uint32_t* ox = P.xout + (size_t)gi * P.n;
-        uint32_t* ov = P.vout + (size_t)gi * P.n;
-        for (int i = t.tid; i < P.n; i += t.nthr) { ox[i] = x[i].a[0]; ov[i] = VALUES ? val[i].a[0] : 0u; }
+        if (P.mvc8) {
+            int8_t* out = const_cast<int8_t*>(P.mvc8);
+            const int nf = (int)min((unsigned long long)32, P.num_frames - f0);
+            for (int i = t.tid; i < P.n; i += t.nthr) {
+                const uint32_t xw = x[i].a[0], vw = VALUES ? val[i].a[0] : 0u;
+                for (int b = 0; b < nf; b++) out[(size_t)(f0 + b) * P.n + i] = ((xw >> b) & 1u) ? 2 : (int8_t)((vw >> b) & 1u);
+            }
+        } else {
+            uint32_t* ox = P.xout + (size_t)gi * P.n;
+            uint32_t* ov = P.vout + (size_t)gi * P.n;
+            for (int i = t.tid; i < P.n; i += t.nthr) { ox[i] = x[i].a[0]; ov[i] = VALUES ? val[i].a[0] : 0u; }
+        }
         team_sync(t);
     }
 }

@@ -9,6 +9,11 @@
 //     coalesced, vectorised ld.global.v4 of four whole 32-byte sectors.
 //   * index arrays (int32, the reference layouts [m][dc], [n][dv]) are streamed once per iteration
 //     and amortised over the 32*R frames of the batch.
+//     They reach the SM through the TMA: every WARP takes tiles of E2_TILE consecutive nodes from a global work
+//     counter and has the int32 lookups of its next tile copied into shared memory by one 1-D bulk copy
+//     (cp.async.bulk.shared.global + mbarrier complete_tx, double-buffered per warp) while it gathers for the
+//     current one, so a gather address never waits for a dependent global load -- the phase is ONE memory latency
+//     deep instead of two, and tiles balance the warps to within 32 nodes.
 //   * one COOPERATIVE persistent kernel per launch: check phase | grid.sync | variable phase |
 //     grid.sync per iteration, termination decided on the device from OR-reduced masks.
 // Bound: HBM bandwidth (state 1.5*n*R*4 B = 192 MB at n = 10^6, R = 32, larger than L2).
@@ -24,10 +29,15 @@ namespace cg = cooperative_groups;
 constexpr int E2_RMAX = 32;
 constexpr int E2_THREADS = 256;
 constexpr int E2_COUNT_SLICE = 4080;  // variables per thread in the per-frame count phase (16 * 255)
+constexpr int E2_TILE = 32;           // nodes per streamed tile of lookups (one warp's tile)
+constexpr int E2_TILE_MAXDEG = 8;     // tiles of 32 x 8 x 4 bytes = 1 KB, two per warp; larger degrees take the plain loops
+constexpr int E2_TILE_BYTES = E2_TILE * E2_TILE_MAXDEG * 4;
 
 struct E2Params {
-    const int* c2v;   // [m][dc]
+    const int* c2v;   // [m][dc]   (padded with zeros to a whole number of tiles when tma != 0)
     const int* v2c;   // [n][dv]
+    int tma;                        // 1: lookups streamed as tiles through the TMA (cp.async.bulk)
+    unsigned long long* tile_ctr;   // global tile work counter, zero at launch, never reset (phases use consecutive ranges)
     int n, m, dv, dc;
     int R;            // words per row (multiple of 4, <= 32)
     uint4* X;         // [n][R/4]
@@ -53,6 +63,82 @@ struct E2Params {
 
 __device__ __forceinline__ uint32_t& q_at(uint4& v, int k) { return reinterpret_cast<uint32_t*>(&v)[k]; }
 
+// ---- TMA tile streaming of the lookups ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA; completion is signalled on the mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// per-WARP streaming state: every warp streams its own tiles (its own two buffers and mbarriers), so warps drift
+// freely as in a plain grid-stride loop -- a block-wide tile (tried first) put two __syncthreads around every 64
+// nodes and measured 9 % slower than no streaming at all
+struct E2Stream {
+    int* buf[2];          // shared: this warp's two tiles of lookups
+    uint64_t* bar;        // shared: this warp's bar[2]
+    uint32_t parity[2];   // phase parity of each buffer's mbarrier
+    unsigned long long base;   // value of the global tile counter at which the current phase starts
+};
+
+// Runs body(node, lookups_of_node_in_shared_memory) for every node of tiles taken from the global counter.
+// Lookups of the NEXT tile are in flight (TMA) while this one is processed; the id of the tile after that is being
+// fetched (global atomic) meanwhile.  Every warp draws exactly two ids past the end, so a phase advances the counter
+// by ntiles + 2 * (warps of the grid) and all warps know the next phase's base without communicating.
+template <class F>
+__device__ __forceinline__ void e2_stream_tiles(const int* gidx, int nodes, int d, int Q, unsigned long long* ctr, E2Stream& st, F&& body) {
+    const long long ntiles = (nodes + E2_TILE - 1) / E2_TILE;
+    const uint32_t tile_bytes = (uint32_t)(E2_TILE * d * 4);
+    const int lane = (int)threadIdx.x & 31;
+    const int per_step = 32 / Q;   // nodes handled per step (a thread owns one 128-bit quad of a row)
+    const int nl0 = lane / Q;
+    auto fetch = [&]() -> long long {   // warp-uniform id of the next tile
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(ctr, 1ull);
+        return (long long)(__shfl_sync(0xFFFFFFFFu, v, 0) - st.base);
+    };
+    auto issue = [&](long long tile, int b) {
+        if (lane == 0) {
+            mbar_expect_tx(&st.bar[b], tile_bytes);
+            bulk_g2s(st.buf[b], gidx + (size_t)tile * E2_TILE * d, tile_bytes, &st.bar[b]);
+        }
+    };
+    long long cur = fetch(), nxt = fetch();
+    if (cur < ntiles) issue(cur, 0);
+    for (int b = 0; cur < ntiles; b ^= 1) {
+        __syncwarp();                          // every lane is done with buffer b^1 (read in the previous step)
+        if (nxt < ntiles) issue(nxt, b ^ 1);
+        unsigned long long pend = 0;           // id of the tile after the next: the atomic is in flight while this tile is
+        if (lane == 0) pend = atomicAdd(ctr, 1ull);   // processed; its result is only looked at afterwards
+        mbar_wait(&st.bar[b], st.parity[b]);
+        st.parity[b] ^= 1u;
+        const int* tile = st.buf[b];
+        const int first = (int)cur * E2_TILE;
+        for (int nl = nl0; nl < E2_TILE; nl += per_step) {
+            const int node = first + nl;
+            if (node < nodes) body(node, tile + nl * d);
+        }
+        cur = nxt; nxt = (long long)(__shfl_sync(0xFFFFFFFFu, pend, 0) - st.base);
+    }
+    st.base += (unsigned long long)ntiles + 2ull * gridDim.x * (blockDim.x >> 5);
+}
+
 // OR-reduce per word column and add-reduce cnt over the block, then one global atomic per column.
 __device__ __forceinline__ void e2_block_accumulate(uint32_t* s_or /*[2*RMAX]*/, uint32_t* s_cnt, uint32_t* g_acc,
                                                     int R, int q, const uint4& any, const uint4& chg, uint32_t cnt) {
@@ -73,14 +159,11 @@ __device__ __forceinline__ void e2_block_accumulate(uint32_t* s_or /*[2*RMAX]*/,
     if (threadIdx.x == 0 && *s_cnt) atomicAdd(&g_acc[2 * E2_RMAX], *s_cnt);
 }
 
-template <bool VALUES>
-__device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads) {
-    const int Q = P.R >> 2;
-    const unsigned long long total = (unsigned long long)P.m * Q;
-    for (unsigned long long t = gtid; t < total; t += gthreads) {
-        const int c = (int)(t / Q), q = (int)(t - (unsigned long long)c * Q);
+// one check, one quad column: two = [>= 2 erased sockets] over the dc gathered rows
+template <bool VALUES, bool SMEM_IDX>
+__device__ __forceinline__ void e2_check_node(const E2Params& P, int Q, unsigned long long t, int q, const int* idx) {
+    {
         uint4 one = make_uint4(0, 0, 0, 0), two = one, par = one;
-        const int* idx = P.c2v + (size_t)c * P.dc;
         // sockets in batches of 8: all row gathers of a batch are in flight before the first is combined
         // (memory-level parallelism; a missing socket contributes the neutral word 0)
         for (int j0 = 0; j0 < P.dc; j0 += 8) {
@@ -90,7 +173,7 @@ __device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long 
                 w[u] = make_uint4(0, 0, 0, 0);
                 if (VALUES) vv[u] = make_uint4(0, 0, 0, 0);
                 if (j0 + u < P.dc) {
-                    const int v = __ldg(idx + j0 + u);
+                    const int v = SMEM_IDX ? idx[j0 + u] : __ldg(idx + j0 + u);
                     w[u] = P.X[(size_t)v * Q + q];
                     if (VALUES) vv[u] = P.V[(size_t)v * Q + q];
                 }
@@ -108,20 +191,29 @@ __device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long 
 }
 
 template <bool VALUES>
-__device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads,
-                                             const uint32_t* s_mask, uint32_t* s_or, uint32_t* s_cnt, uint32_t* g_acc) {
+__device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads, E2Stream& st) {
     const int Q = P.R >> 2;
-    const unsigned long long total = (unsigned long long)P.n * Q;
-    uint4 any = make_uint4(0, 0, 0, 0), chg = any;
-    uint32_t cnt = 0;
-    int myq = 0;
-    // gthreads is a multiple of Q (host guarantees), so a thread keeps the same quad column
+    if (P.tma) {
+        const int q = (int)threadIdx.x % Q;
+        e2_stream_tiles(P.c2v, P.m, P.dc, Q, P.tile_ctr, st, [&](int c, const int* idx) {
+            e2_check_node<VALUES, true>(P, Q, (unsigned long long)c * Q + q, q, idx);
+        });
+        return;
+    }
+    const unsigned long long total = (unsigned long long)P.m * Q;
     for (unsigned long long t = gtid; t < total; t += gthreads) {
-        const int i = (int)(t / Q), q = (int)(t - (unsigned long long)i * Q);
-        myq = q;
+        const int c = (int)(t / Q), q = (int)(t - (unsigned long long)c * Q);
+        e2_check_node<VALUES, false>(P, Q, t, q, P.c2v + (size_t)c * P.dc);
+    }
+}
+
+// one variable, one quad column: x &= AND of the dv gathered `two` rows; accumulates any / chg / cnt
+template <bool VALUES, bool SMEM_IDX>
+__device__ __forceinline__ void e2_var_node(const E2Params& P, int Q, unsigned long long t, int q, const int* idx,
+                                            const uint32_t* s_mask, uint4& any, uint4& chg, uint32_t& cnt) {
+    {
         const uint4 xi = P.X[t];
         uint4 xn = xi, nv = make_uint4(0, 0, 0, 0);
-        const int* idx = P.v2c + (size_t)i * P.dv;
         for (int j0 = 0; j0 < P.dv; j0 += 4) {   // batches of 4 gathers in flight; neutral word = all ones
             uint4 tw[4], pr[4];
 #pragma unroll
@@ -129,7 +221,7 @@ __device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long lo
                 tw[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                 if (VALUES) pr[u] = make_uint4(0, 0, 0, 0);
                 if (j0 + u < P.dv) {
-                    const int c = __ldg(idx + j0 + u);
+                    const int c = SMEM_IDX ? idx[j0 + u] : __ldg(idx + j0 + u);
                     tw[u] = P.T[(size_t)c * Q + q];
                     if (VALUES) pr[u] = P.PAR[(size_t)c * Q + q];
                 }
@@ -155,6 +247,29 @@ __device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long lo
         chg.x |= xi.x ^ xn.x; chg.y |= xi.y ^ xn.y; chg.z |= xi.z ^ xn.z; chg.w |= xi.w ^ xn.w;
         cnt += __popc(xn.x & s_mask[q * 4]) + __popc(xn.y & s_mask[q * 4 + 1]) + __popc(xn.z & s_mask[q * 4 + 2]) +
                __popc(xn.w & s_mask[q * 4 + 3]);
+    }
+}
+
+template <bool VALUES>
+__device__ __forceinline__ void e2_var_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads,
+                                             const uint32_t* s_mask, uint32_t* s_or, uint32_t* s_cnt, uint32_t* g_acc, E2Stream& st) {
+    const int Q = P.R >> 2;
+    uint4 any = make_uint4(0, 0, 0, 0), chg = any;
+    uint32_t cnt = 0;
+    int myq = 0;
+    if (P.tma) {
+        myq = (int)threadIdx.x % Q;   // blockDim.x is a multiple of Q: a thread keeps its quad column
+        e2_stream_tiles(P.v2c, P.n, P.dv, Q, P.tile_ctr, st, [&](int i, const int* idx) {
+            e2_var_node<VALUES, true>(P, Q, (unsigned long long)i * Q + myq, myq, idx, s_mask, any, chg, cnt);
+        });
+    } else {
+        const unsigned long long total = (unsigned long long)P.n * Q;
+        // gthreads is a multiple of Q (host guarantees), so a thread keeps the same quad column
+        for (unsigned long long t = gtid; t < total; t += gthreads) {
+            const int i = (int)(t / Q), q = (int)(t - (unsigned long long)i * Q);
+            myq = q;
+            e2_var_node<VALUES, false>(P, Q, t, q, P.v2c + (size_t)i * P.dv, s_mask, any, chg, cnt);
+        }
     }
     e2_block_accumulate(s_or, s_cnt, g_acc, P.R, myq, any, chg, cnt);
 }
@@ -201,6 +316,19 @@ __global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant
     __shared__ uint32_t s_valid[E2_RMAX];
     __shared__ uint32_t s_any[E2_RMAX];
     __shared__ uint32_t s_flag;
+    __shared__ __align__(128) int s_tile[E2_THREADS / 32][2][E2_TILE_BYTES / 4];
+    __shared__ __align__(8) uint64_t s_bar[E2_THREADS / 32][2];
+    E2Stream st;
+    {
+        const int wb = (int)threadIdx.x >> 5;
+        st.buf[0] = s_tile[wb][0]; st.buf[1] = s_tile[wb][1]; st.bar = s_bar[wb];
+        st.parity[0] = 0u; st.parity[1] = 0u; st.base = 0ull;
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(&st.bar[0], 1u); mbar_init(&st.bar[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     const int R = P.R, Q = R >> 2;
     const int ACC = 2 * E2_RMAX + 1;
@@ -288,10 +416,10 @@ __global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant
                 if (pass == 0) for (int w = 0; w < R; w++) exec_sum += __popc(s_running[w]);
                 if (DECODE && blockIdx.x == 0)   // only block 0 reads framecnt, and it is past those reads
                     for (int f = threadIdx.x; f < 32 * E2_RMAX; f += blockDim.x) P.framecnt[f] = 0;
-                e2_check_phase<VALUES>(P, gtid, gthreads);
+                e2_check_phase<VALUES>(P, gtid, gthreads, st);
                 zero_block_acc();
                 grid.sync();
-                e2_var_phase<VALUES>(P, gtid, gthreads, s_mask, s_or, &s_cnt, P.acc + par * ACC);
+                e2_var_phase<VALUES>(P, gtid, gthreads, s_mask, s_or, &s_cnt, P.acc + par * ACC, st);
                 zero_global_acc(par ^ 1);   // everyone finished reading it before the sync above
                 grid.sync();
                 if (DECODE) {

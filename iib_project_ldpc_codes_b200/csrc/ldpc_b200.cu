@@ -16,6 +16,10 @@
 #include <utility>
 #include <new>
 #include <exception>
+#include <thread>
+#include <memory>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/ldpc_b200.h"
 #include "e1_kernels.cuh"
@@ -107,17 +111,24 @@ struct ldpc_b200_graph {
     int sm_count = 0, smem_optin = 0;
     // bank-conflict-aware placements for the Monte-Carlo kernel, one per words-per-group (index = words)
     struct Placed {
-        bool ready = false;
-        int effort = 0;
+        bool ready = false;            // device arrays below are valid
+        int effort = 0;                // effort of the placement on the device
         uint16_t* d_c2v = nullptr; uint16_t* d_v2c = nullptr; uint16_t* d_var_orig = nullptr;
         double wf_natural = 0, wf_placed = 0, wf_ideal = 0;
+        // background search (relabel.cpp runs on host threads while the GPU already decodes on the natural layout)
+        std::thread worker;
+        std::atomic<int> state{0};     // 0 idle, 1 searching, 2 result waiting to be uploaded
+        int search_effort = 0;
+        int source = 0;                // 1 = searched in this process, 2 = read from the disk cache
+        std::unique_ptr<Placement> result;
     } placed[5];
+    uint64_t graph_hash = 0;           // content hash (dims + lookups), keys the placement cache on disk
     int place_effort = -1;  // -1: LDPC_B200_PLACE_EFFORT or default
     // E2 (HBM/L2-streamed engine): int32 lookups in the reference layouts + frame-minor state rows
     int* d_c2v32 = nullptr; int* d_v2c32 = nullptr;
     void* e2_X = nullptr; void* e2_T = nullptr; void* e2_V = nullptr; void* e2_PAR = nullptr;
     size_t e2_xbytes = 0, e2_vbytes = 0;
-    uint32_t* e2_acc = nullptr; uint32_t* e2_framecnt = nullptr;
+    uint32_t* e2_acc = nullptr; uint32_t* e2_framecnt = nullptr; unsigned long long* e2_tilectr = nullptr;
     unsigned long long* e2_hbuf = nullptr; size_t e2_hbuf_cap = 0;
     int engine = 0;  // 0 auto, 1 force E1, 2 force E2
     // staged E1 Monte-Carlo: cut points per (eps list, cap, words), spill buffers, per-stage record counts
@@ -126,6 +137,10 @@ struct ldpc_b200_graph {
     uint32_t* d_idlist = nullptr; size_t idlist_bytes = 0;   // expurgated runs: frames listed for the re-count pass
     unsigned long long* d_stage_cnt = nullptr; size_t stage_cnt_cap = 0;
     // batched decode buffers (cached between calls)
+    // single-group decode (<= 32 frames: the message_passing drop-in): one pinned host block and one device block
+    // [symbols | errors | ret], one upload, ONE kernel, one download
+    void* fast_pin = nullptr; void* fast_dev = nullptr; size_t fast_cap = 0;
+    std::mutex mu;   // serialises calls on this handle (the drop-in may be called from several host threads)
     void* dec_mvc = nullptr; void* dec_x = nullptr; void* dec_v = nullptr; void* dec_err = nullptr; void* dec_ret = nullptr;
     size_t dec_mvc_cap = 0, dec_x_cap = 0, dec_v_cap = 0, dec_err_cap = 0, dec_ret_cap = 0;
     int launches = 0;      // kernels launched since the last stats read
@@ -159,11 +174,11 @@ static int tuning_env(const char* name) {
 
 // Plan with the socket lists in tensor memory (e1_tmem.cuh): shared memory holds state only; every thread's gather
 // addresses must fit its warp's share of the 512 TMEM columns (4 lane quarters x 512 columns x 32 lanes).
-static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg) {
+static bool plan_e1_tm(const ldpc_b200_graph* g, int cap, E1Config& cfg, int force_words = 0) {
     if (!((g->dv == 3 && g->dc == 6) || (g->dv == 4 && g->dc == 8))) return false;   // degree pairs the kernels are specialised for
     if (g->n > 65535 || tuning_env("LDPC_B200_TMEM") == 2) return false;
     const uint32_t limit = (uint32_t)g->smem_optin - 64;   // the kernels' static shared memory (the TMEM base slot)
-    const int want_words = g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS");
+    const int want_words = force_words ? force_words : (g->tune_words ? g->tune_words : tuning_env("LDPC_B200_WORDS"));
     const int want_teams = g->tune_teams ? g->tune_teams : tuning_env("LDPC_B200_TEAMS");
     const int want_tw = g->tune_team_warps ? g->tune_team_warps : tuning_env("LDPC_B200_TEAM_WARPS");
     const int cand[3] = {4, 2, 1};
@@ -412,15 +427,18 @@ extern "C" int ldpc_b200_graph_create(const int* v2c, const int* c2v, int n, int
 
 extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     if (!g) return;
+    for (auto& pl : g->placed) if (pl.worker.joinable()) pl.worker.join();
     cudaSetDevice(g->device);
     cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
     cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
     for (int i = 0; i < ldpc_b200_graph::BEC_RING; i++) { if (g->h_bec[i]) cudaFreeHost(g->h_bec[i]); if (g->h_bec_ev[i]) cudaEventDestroy(g->h_bec_ev[i]); }
     for (auto& pl : g->placed) { cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
     cudaFree(g->d_c2v32); cudaFree(g->d_v2c32); cudaFree(g->e2_X); cudaFree(g->e2_T); cudaFree(g->e2_V); cudaFree(g->e2_PAR);
-    cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf);
+    cudaFree(g->e2_acc); cudaFree(g->e2_framecnt); cudaFree(g->e2_hbuf); cudaFree(g->e2_tilectr);
     cudaFree(g->d_spill[0]); cudaFree(g->d_spill[1]); cudaFree(g->d_stage_cnt); cudaFree(g->d_idlist);
     cudaFree(g->dec_mvc); cudaFree(g->dec_x); cudaFree(g->dec_v); cudaFree(g->dec_err); cudaFree(g->dec_ret);
+    if (g->fast_pin) cudaFreeHost(g->fast_pin);
+    cudaFree(g->fast_dev);
     if (g->ev_init) for (int i = 0; i < ldpc_b200_graph::RING; i++) { cudaEventDestroy(g->ev0[i]); cudaEventDestroy(g->ev1[i]); }
     delete g;
 }
@@ -429,14 +447,24 @@ extern "C" int ldpc_b200_set_place_effort(ldpc_b200_graph* g, int effort) {
     if (!g) return fail(LDPC_B200_EINVAL, "set_place_effort: NULL graph");
     g->place_effort = effort;
     for (auto& pl : g->placed) {
+        if (pl.worker.joinable()) pl.worker.join();
         cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig);
-        pl = ldpc_b200_graph::Placed();
+        pl.d_c2v = pl.d_v2c = pl.d_var_orig = nullptr;
+        pl.ready = false; pl.effort = 0; pl.state.store(0); pl.result.reset();
     }
     return LDPC_B200_OK;
 }
 
+static int ensure_placement(ldpc_b200_graph* g, int words, double frames, bool wait);
+
 extern "C" int ldpc_b200_placement_info(ldpc_b200_graph* g, int words, double* natural, double* placed, double* ideal) {
-    if (!g || words < 1 || words > 4 || !g->placed[words].ready) return fail(LDPC_B200_EINVAL, "placement_info: no placement for words=%d yet", words);
+    if (!g || words < 1 || words > 4) return fail(LDPC_B200_EINVAL, "placement_info: bad argument");
+    if (g->placed[words].state.load() != 0) {   // a background search is running or has just finished: take its result
+        CUDA_TRY(cudaSetDevice(g->device));
+        const int rc = ensure_placement(g, words, 0.0, true);
+        if (rc) return rc;
+    }
+    if (!g->placed[words].ready) return fail(LDPC_B200_EINVAL, "placement_info: no placement for words=%d yet", words);
     if (natural) *natural = g->placed[words].wf_natural;
     if (placed) *placed = g->placed[words].wf_placed;
     if (ideal) *ideal = g->placed[words].wf_ideal;
@@ -514,12 +542,134 @@ static int ensure_events(ldpc_b200_graph* g) {
     return LDPC_B200_OK;
 }
 
-// Build (once) the shared-memory placement of the graph for `words` words per node (relabel.hpp).
+// ---- shared-memory placement of the graph for `words` words per node (relabel.hpp) --------------------------------
+// The search costs 0.5 s (n = 1000) to a few seconds (n = 10^4) of host threads.  It no longer delays the first call:
+//   * a finished placement is kept on disk, keyed by the graph's content hash, word width and effort
+//     ($LDPC_B200_CACHE_DIR, else $XDG_CACHE_HOME/ldpc_b200, else ~/.cache/ldpc_b200; LDPC_B200_CACHE=0 disables it),
+//     and verified against the graph when it is read back (a relabelling that does not match is ignored);
+//   * otherwise the search runs on a background thread while the GPU decodes on the NATURAL layout (same results by
+//     construction: the channel generator is keyed by original variable ids); launches pick the placed layout up as
+//     soon as it is there -- between the frame chunks of a staged run, or at the next call.
+// LDPC_B200_PLACE_SYNC=1 restores the blocking behaviour (tests that measure the placed kernels).
 // `frames` = frames the caller is about to decode (all points): only a very long run pays for a longer placement
 // search by itself (n = 1000: effort 24 takes 1.9 s on the host instead of 0.5 s and removes about a fifth of the
 // remaining conflict replays, ~1 % of the run time); callers that reuse a handle set it with ldpc_b200_set_place_effort.
-static int ensure_placement(ldpc_b200_graph* g, int words, double frames) {
+static uint64_t fnv1a64(const void* data, size_t bytes, uint64_t h) {   // 8 bytes per step: this hashes megabytes
+    const unsigned char* p = (const unsigned char*)data;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h ^= w; h *= 1099511628211ull; h ^= h >> 29; }
+    for (; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static uint64_t graph_content_hash(ldpc_b200_graph* g) {
+    if (!g->graph_hash) {
+        uint64_t h = 1469598103934665603ull;
+        const int dims[4] = {g->n, g->k, g->dv, g->dc};
+        h = fnv1a64(dims, sizeof dims, h);
+        h = fnv1a64(g->v2c.data(), g->v2c.size() * sizeof(int), h);
+        h = fnv1a64(g->c2v.data(), g->c2v.size() * sizeof(int), h);
+        g->graph_hash = h ? h : 1;
+    }
+    return g->graph_hash;
+}
+
+static std::string place_cache_path(ldpc_b200_graph* g, int words, int effort) {
+    const char* off = getenv("LDPC_B200_CACHE");
+    if (off && atoi(off) == 0 && off[0] == '0') return "";
+    std::string dir;
+    if (const char* d = getenv("LDPC_B200_CACHE_DIR")) dir = d;
+    else if (const char* x = getenv("XDG_CACHE_HOME")) dir = std::string(x) + "/ldpc_b200";
+    else if (const char* h = getenv("HOME")) dir = std::string(h) + "/.cache/ldpc_b200";
+    else return "";
+    char name[128];
+    snprintf(name, sizeof name, "/place_%016llx_w%d_e%d.bin", (unsigned long long)graph_content_hash(g), words, effort);
+    return dir + name;
+}
+
+static void mkdirs(const std::string& dir) {
+    for (size_t i = 1; i <= dir.size(); i++)
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+}
+
+struct PlaceFileHeader { uint32_t magic, version; int32_t n, m, dv, dc, B, effort; uint64_t hash; double wf[3]; };
+static constexpr uint32_t kPlaceMagic = 0x4C50424Cu;   // "LBPL"
+
+static void place_cache_store(ldpc_b200_graph* g, int words, int effort, const Placement& P) {
+    const std::string path = place_cache_path(g, words, effort);
+    if (path.empty()) return;
+    mkdirs(path.substr(0, path.rfind('/')));
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    PlaceFileHeader H = {kPlaceMagic, 1u, g->n, g->m, g->dv, g->dc, 32 / words, effort, graph_content_hash(g),
+                         {P.wavefronts_natural, P.wavefronts_placed, P.wavefronts_ideal}};
+    bool ok = fwrite(&H, sizeof H, 1, f) == 1;
+    auto put = [&](const std::vector<int>& v) { ok = ok && fwrite(v.data(), sizeof(int), v.size(), f) == v.size(); };
+    put(P.var_slot); put(P.chk_slot); put(P.c2v); put(P.v2c); put(P.var_orig);
+    ok = (fclose(f) == 0) && ok;
+    if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+
+// reads a cached placement and VERIFIES that it is a relabelling of this graph (nothing on disk is trusted)
+static bool place_cache_load(ldpc_b200_graph* g, int words, int effort, Placement& P) {
+    const std::string path = place_cache_path(g, words, effort);
+    if (path.empty()) return false;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    PlaceFileHeader H;
+    bool ok = fread(&H, sizeof H, 1, f) == 1 && H.magic == kPlaceMagic && H.version == 1u && H.n == g->n && H.m == g->m &&
+              H.dv == g->dv && H.dc == g->dc && H.B == 32 / words && H.effort == effort && H.hash == graph_content_hash(g);
+    const size_t n = (size_t)g->n, m = (size_t)g->m, E = n * g->dv;
+    auto get = [&](std::vector<int>& v, size_t cnt) { v.resize(cnt); ok = ok && fread(v.data(), sizeof(int), cnt, f) == cnt; };
+    if (ok) { get(P.var_slot, n); get(P.chk_slot, m); get(P.c2v, E); get(P.v2c, E); get(P.var_orig, n); }
+    fclose(f);
+    if (!ok) return false;
+    // var_slot / chk_slot are permutations, var_orig inverts var_slot, and every node's neighbour multiset maps over
+    std::vector<char> seen(std::max(n, m), 0);
+    for (size_t i = 0; i < n; i++) { const int s = P.var_slot[i]; if (s < 0 || (size_t)s >= n || seen[s] || P.var_orig[s] != (int)i) return false; seen[s] = 1; }
+    std::fill(seen.begin(), seen.end(), 0);
+    for (size_t c = 0; c < m; c++) { const int s = P.chk_slot[c]; if (s < 0 || (size_t)s >= m || seen[s]) return false; seen[s] = 1; }
+    std::vector<int> a, b;
+    for (size_t c = 0; c < m; c++) {
+        a.clear(); b.clear();
+        for (int j = 0; j < g->dc; j++) { a.push_back(P.var_slot[g->c2v[c * g->dc + j]]); b.push_back(P.c2v[(size_t)P.chk_slot[c] * g->dc + j]); }
+        std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+        if (a != b) return false;
+    }
+    for (size_t i = 0; i < n; i++) {
+        a.clear(); b.clear();
+        for (int j = 0; j < g->dv; j++) { a.push_back(P.chk_slot[g->v2c[i * g->dv + j]]); b.push_back(P.v2c[(size_t)P.var_slot[i] * g->dv + j]); }
+        std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+        if (a != b) return false;
+    }
+    P.n = g->n; P.m = g->m; P.dv = g->dv; P.dc = g->dc; P.B = 32 / words;
+    P.wavefronts_natural = H.wf[0]; P.wavefronts_placed = H.wf[1]; P.wavefronts_ideal = H.wf[2];
+    return true;
+}
+
+static int placement_upload(ldpc_b200_graph* g, int words, int effort, const Placement& P) {
     ldpc_b200_graph::Placed& pl = g->placed[words];
+    std::vector<uint16_t> h_c((size_t)g->dc * g->m_pad, 0), h_v((size_t)g->dv * g->n_pad, 0), h_o((size_t)g->n_pad, 0);
+    for (int c = 0; c < g->m; c++) for (int j = 0; j < g->dc; j++) h_c[sock_off(g->dc, g->m_pad, j, c)] = (uint16_t)P.c2v[(size_t)c * g->dc + j];
+    for (int i = 0; i < g->n; i++) for (int j = 0; j < g->dv; j++) h_v[sock_off(g->dv, g->n_pad, j, i)] = (uint16_t)P.v2c[(size_t)i * g->dv + j];
+    for (int i = 0; i < g->n; i++) h_o[i] = (uint16_t)P.var_orig[i];
+    const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16), bo = align_up((uint32_t)(h_o.size() * 2), 16);
+    // launches already in flight may still read the previous arrays: the old ones are released only after the device is idle
+    uint16_t *nc = nullptr, *nv = nullptr, *no = nullptr;
+    CUDA_TRY(cudaMalloc(&nc, bc)); CUDA_TRY(cudaMalloc(&nv, bv)); CUDA_TRY(cudaMalloc(&no, bo));
+    CUDA_TRY(cudaMemset(nc, 0, bc)); CUDA_TRY(cudaMemset(nv, 0, bv));
+    CUDA_TRY(cudaMemcpy(nc, h_c.data(), h_c.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(nv, h_v.data(), h_v.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(no, h_o.data(), h_o.size() * 2, cudaMemcpyHostToDevice));
+    if (pl.ready) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig); }
+    pl.d_c2v = nc; pl.d_v2c = nv; pl.d_var_orig = no;
+    pl.wf_natural = P.wavefronts_natural; pl.wf_placed = P.wavefronts_placed; pl.wf_ideal = P.wavefronts_ideal;
+    pl.ready = true; pl.effort = effort;
+    return LDPC_B200_OK;
+}
+
+static int placement_effort(const ldpc_b200_graph* g, double frames) {
     int effort = g->place_effort;
     if (effort < 0) {
         const char* s = getenv("LDPC_B200_PLACE_EFFORT");
@@ -529,26 +679,86 @@ static int ensure_placement(ldpc_b200_graph* g, int words, double frames) {
             if (frames * (double)g->n >= 2e13) effort = std::max(6, std::min(24, 24000 / std::max(1, g->n)));
         }
     }
-    if (pl.ready && pl.effort >= effort) return LDPC_B200_OK;
-    if (pl.ready) {   // a bigger run than the one the placement was made for: search again
-        cudaFree(pl.d_c2v); cudaFree(pl.d_v2c); cudaFree(pl.d_var_orig);
-        pl.d_c2v = pl.d_v2c = pl.d_var_orig = nullptr; pl.ready = false;
+    return effort;
+}
+
+// Makes progress towards a placement of at least the wanted effort without blocking (unless wait is set): takes a
+// finished background search or a cached file, or starts the search.  Afterwards g->placed[words].ready says whether
+// a placed layout (of any effort) is on the device; callers fall back to the natural layout when it is not.
+static int ensure_placement(ldpc_b200_graph* g, int words, double frames, bool wait) {
+    ldpc_b200_graph::Placed& pl = g->placed[words];
+    const int effort = placement_effort(g, frames);
+    if (tuning_env("LDPC_B200_PLACE_SYNC") == 1) wait = true;
+    for (;;) {
+        if (pl.ready && pl.effort >= effort && pl.state.load() == 0) return LDPC_B200_OK;
+        const int st = pl.state.load(std::memory_order_acquire);
+        if (st == 2) {   // a search has finished: upload its result
+            if (pl.worker.joinable()) pl.worker.join();
+            std::unique_ptr<Placement> R = std::move(pl.result);
+            pl.state.store(0);
+            if (R && (!pl.ready || pl.search_effort > pl.effort)) {
+                const int rc = placement_upload(g, words, pl.search_effort, *R);
+                if (rc) return rc;
+                pl.source = 1;
+            }
+            continue;
+        }
+        if (st == 1) {   // searching
+            if (!wait) return LDPC_B200_OK;
+            if (pl.worker.joinable()) pl.worker.join();
+            continue;
+        }
+        // idle and nothing good enough yet: disk cache first, else start a search
+        if (effort <= 0) {   // effort 0 = natural layout, "placed" trivially
+            Placement P;
+            place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, 0, 0x5EEDull, P);
+            return placement_upload(g, words, 0, P);
+        }
+        {
+            Placement P;
+            if (place_cache_load(g, words, effort, P)) { const int rc = placement_upload(g, words, effort, P); if (rc) return rc; pl.source = 2; continue; }
+        }
+        graph_content_hash(g);   // computed on this thread: the worker only reads it
+        pl.search_effort = effort;
+        pl.state.store(1);
+        try {
+            pl.worker = std::thread([g, words, effort, &pl]() {
+                std::unique_ptr<Placement> R(new Placement());
+                place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, *R);
+                place_cache_store(g, words, effort, *R);
+                pl.result = std::move(R);
+                pl.state.store(2, std::memory_order_release);
+            });
+        } catch (...) {   // no thread to be had: search here
+            pl.state.store(0);
+            Placement P;
+            place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, P);
+            place_cache_store(g, words, effort, P);
+            pl.source = 1;
+            return placement_upload(g, words, effort, P);
+        }
+        if (!wait) return LDPC_B200_OK;
     }
-    Placement P;
-    place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, P);
-    std::vector<uint16_t> h_c((size_t)g->dc * g->m_pad, 0), h_v((size_t)g->dv * g->n_pad, 0), h_o((size_t)g->n_pad, 0);
-    for (int c = 0; c < g->m; c++) for (int j = 0; j < g->dc; j++) h_c[sock_off(g->dc, g->m_pad, j, c)] = (uint16_t)P.c2v[(size_t)c * g->dc + j];
-    for (int i = 0; i < g->n; i++) for (int j = 0; j < g->dv; j++) h_v[sock_off(g->dv, g->n_pad, j, i)] = (uint16_t)P.v2c[(size_t)i * g->dv + j];
-    for (int i = 0; i < g->n; i++) h_o[i] = (uint16_t)P.var_orig[i];
-    const size_t bc = align_up((uint32_t)(h_c.size() * 2), 16), bv = align_up((uint32_t)(h_v.size() * 2), 16), bo = align_up((uint32_t)(h_o.size() * 2), 16);
-    CUDA_TRY(cudaMalloc(&pl.d_c2v, bc)); CUDA_TRY(cudaMalloc(&pl.d_v2c, bv)); CUDA_TRY(cudaMalloc(&pl.d_var_orig, bo));
-    CUDA_TRY(cudaMemset(pl.d_c2v, 0, bc)); CUDA_TRY(cudaMemset(pl.d_v2c, 0, bv));
-    CUDA_TRY(cudaMemcpy(pl.d_c2v, h_c.data(), h_c.size() * 2, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(pl.d_v2c, h_v.data(), h_v.size() * 2, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(pl.d_var_orig, h_o.data(), h_o.size() * 2, cudaMemcpyHostToDevice));
-    pl.wf_natural = P.wavefronts_natural; pl.wf_placed = P.wavefronts_placed; pl.wf_ideal = P.wavefronts_ideal;
-    pl.ready = true; pl.effort = effort;
-    return LDPC_B200_OK;
+}
+
+// Blocks until no placement search of this handle is running and every finished one is on the device.  source (may be
+// NULL) receives, for `words` (1, 2 or 4; 0 = skip): 0 = no placement, 1 = searched in this process, 2 = disk cache.
+extern "C" int ldpc_b200_placement_wait(ldpc_b200_graph* g, int words, int* source) {
+    if (!g || words < 0 || words > 4) return fail(LDPC_B200_EINVAL, "placement_wait: bad argument");
+    return guarded("placement_wait", [&] {
+        CUDA_TRY(cudaSetDevice(g->device));
+        for (int w = 1; w <= 4; w++)
+            if (g->placed[w].state.load() != 0) { const int rc = ensure_placement(g, w, 0.0, true); if (rc) return rc; }
+        if (source) *source = words ? (g->placed[words].ready ? g->placed[words].source : 0) : 0;
+        return (int)LDPC_B200_OK;
+    });
+}
+
+// kernel parameters of the layout to decode on right now: the placed one if it is on the device, else the natural one
+static void use_layout(const ldpc_b200_graph* g, int words, E1Params& P) {
+    const ldpc_b200_graph::Placed& pl = g->placed[words];
+    if (pl.ready) { P.c2v = pl.d_c2v; P.v2c = pl.d_v2c; P.var_orig = pl.d_var_orig; }
+    else { P.c2v = g->d_c2v16; P.v2c = g->d_v2c16; P.var_orig = nullptr; }
 }
 
 // Scratch device buffers of the handle-less entry points.  cudaMalloc / cudaFree cost milliseconds (and now and
@@ -624,6 +834,13 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
     const bool use_e2 = weng == 2 || !fits_e1;
 
     const int cap = iterations;
+    // One W = 128 team owns the SM but leaves no room for a staged pattern (n = 6000 .. 9000): a W = 64 team with the
+    // channel draw overlapped (e1_overlap.cuh) is faster (n = 8000: 4.95 -> 5.23e13 edge updates/s, n = 6000: +2 %) --
+    // with the socket lists in tensor memory the word width no longer changes the shared-memory traffic per frame.
+    if (!use_e2 && cfg.tm && cfg.words == 4 && cfg.teams == 1 && num_frames >= 8192 && !g->tune_words && !tuning_env("LDPC_B200_WORDS")) {
+        E1Config ov, alt;
+        if (!plan_e1_overlap(g, cap, cfg, ov) && plan_e1_tm(g, cap, alt, 2) && alt.teams == 1 && plan_e1_overlap(g, cap, alt, ov)) cfg = alt;
+    }
     const size_t raw_words = (size_t)npoints * raw_stride(cap);
     if (g->raw_cap < raw_words) {
         cudaFree(g->d_raw); g->d_raw = nullptr; g->raw_cap = 0;
@@ -671,12 +888,12 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
         return LDPC_B200_OK;
     }
     {
-        int rcp = ensure_placement(g, cfg.words, (double)num_frames * npoints);
+        int rcp = ensure_placement(g, cfg.words, (double)num_frames * npoints, false);
         if (rcp) return rcp;
     }
     E1Params P;
     fill_params(g, cfg, cap, P);
-    P.c2v = g->placed[cfg.words].d_c2v; P.v2c = g->placed[cfg.words].d_v2c; P.var_orig = g->placed[cfg.words].d_var_orig;
+    use_layout(g, cfg.words, P);
     const unsigned long long W = 32ull * cfg.words;
     P.bec = g->d_bec; P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.npoints = npoints; P.expurgation = expurgation;
     philox_round_keys(P.seed_lo, P.seed_hi, P.rk);
@@ -845,12 +1062,65 @@ static int grow(void** p, size_t* cap, size_t bytes) {
     return LDPC_B200_OK;
 }
 
+// Decode of at most 32 frames (one frame group) in ONE kernel launch: symbols go up and results come down through one
+// pinned block each way, nothing else synchronises.  This is what a message_passing() call costs on the GPU.
+static int decode_small(ldpc_b200_graph* g, const E1Config& cfg, bool values, int8_t* Mvc, int frames, int iterations,
+                        int* errors, int* ret) {
+    const size_t nsym = (size_t)frames * g->n;
+    const size_t off_err = (nsym + 15) / 16 * 16, off_ret = off_err + (size_t)frames * std::max(iterations, 1) * 4;
+    const size_t total = off_ret + (size_t)frames * 4;
+    if (g->fast_cap < total) {
+        if (g->fast_pin) cudaFreeHost(g->fast_pin);
+        cudaFree(g->fast_dev);
+        g->fast_pin = g->fast_dev = nullptr; g->fast_cap = 0;
+        const size_t cap_bytes = std::max<size_t>(total, 65536);
+        CUDA_TRY(cudaMallocHost(&g->fast_pin, cap_bytes));
+        CUDA_TRY(cudaMalloc(&g->fast_dev, cap_bytes));
+        g->fast_cap = cap_bytes;
+    }
+    unsigned char* hp = (unsigned char*)g->fast_pin;
+    unsigned char* dp = (unsigned char*)g->fast_dev;
+    memcpy(hp, Mvc, nsym);
+    CUDA_TRY(cudaMemcpyAsync(dp, hp, nsym, cudaMemcpyHostToDevice, 0));
+    E1Config one = cfg;   // ONE group: one team of all the warps (same shared-memory map, the other teams' regions stay unused)
+    one.teams = 1; one.team_warps = E1_MAX_THREADS / 32;
+    E1Params P;
+    fill_params(g, one, iterations, P);
+    P.num_frames = (unsigned long long)frames; P.groups_per_point = 1;
+    P.mvc8 = (const int8_t*)dp;
+    P.errors = (int*)(dp + off_err); P.ret = (int*)(dp + off_ret);
+    const int block = one.teams * one.team_warps * 32;
+    cudaError_t e = values ? launch_decode<true>(P, 1, block, cfg.smem, 0) : launch_decode<false>(P, 1, block, cfg.smem, 0);
+    if (e != cudaSuccess) return fail(LDPC_B200_ECUDA, "decode: kernel launch failed: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaMemcpyAsync(hp, dp, total, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    memcpy(Mvc, hp, nsym);
+    if (iterations > 0) memcpy(errors, hp + off_err, (size_t)frames * iterations * 4);
+    memcpy(ret, hp + off_ret, (size_t)frames * 4);
+    g->launches += 1;
+    return LDPC_B200_OK;
+}
+
 static int ldpc_b200_decode_batch_impl(ldpc_b200_graph* g, int8_t* Mvc, uint64_t frames, int iterations,
                                       int* errors, int* ret) {
     if (!g || !Mvc || !ret || (!errors && iterations > 0)) return fail(LDPC_B200_EINVAL, "decode_batch: NULL argument");
     if (iterations < 0) return fail(LDPC_B200_EINVAL, "decode_batch: iterations < 0");
     if (frames == 0) return LDPC_B200_OK;
+    std::lock_guard<std::mutex> handle_lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    if (frames <= 32 && want_engine(g) != 2 && iterations > 0) {
+        // one frame group: symbols are checked on the host (a few KB), then one launch does everything
+        const size_t nsym = (size_t)frames * g->n;
+        bool values = false;
+        for (size_t i = 0; i < nsym; i++) {
+            const int8_t sym = Mvc[i];
+            if (sym < 0 || sym > 2)
+                return fail(LDPC_B200_EINVAL, "decode_batch: symbol %d at frame %zu position %zu is outside {0,1,2}", (int)sym, i / g->n, i % g->n);
+            values |= (sym == 1);
+        }
+        E1Config cfg;
+        if (plan_e1(g, iterations, values, true, cfg)) return decode_small(g, cfg, values, Mvc, (int)frames, iterations, errors, ret);
+    }
     // chunks of at most 2^20 frames (device buffers are cached in the handle and reused)
     const uint64_t chunk_frames = std::min<uint64_t>(frames, std::max<uint64_t>(1024, std::min<uint64_t>(1ull << 20, (1ull << 31) / (uint64_t)std::max(g->n, 1))));
     const size_t cb = (size_t)chunk_frames * g->n;
@@ -1001,15 +1271,25 @@ extern "C" int ldpc_b200_smem_probe(int device, double* gbytes_per_s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// message_passing.c:7 drop-in.  Device copies of the graph are cached by content hash because the
-// reference passes the same lookups for every frame in fixed-code mode (parallel_simulator.py:360).
+// message_passing.c:7 drop-in.  Device copies of the graph are cached by content because the reference passes the
+// same lookups for every frame in fixed-code mode (parallel_simulator.py:360) -- in freshly made numpy arrays, so the
+// pointers say nothing.  A call finds its handle by a SAMPLED hash of the lookups (64 probes, ~100 ns) followed by a
+// full memcmp against the handle's host copy (24 KB at n = 1000: ~1 us; a byte-wise hash of both arrays cost 50 us per
+// call); at most 16 handles are kept, the least recently used one is dropped; the global lock covers the table only,
+// GPU work runs under the handle's own lock.
 static std::mutex g_cache_mutex;
-struct CacheEntry { ldpc_b200_graph* g; uint64_t hash; };
-static std::unordered_map<uint64_t, ldpc_b200_graph*> g_cache;
+struct CacheEntry { ldpc_b200_graph* g; uint64_t key; uint64_t tick; int users; };
+static std::vector<CacheEntry> g_cache;
+static uint64_t g_cache_tick = 0;
+static constexpr size_t kCacheMax = 16;
 
-static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
-    const unsigned char* p = (const unsigned char*)data;
-    for (size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+static uint64_t sampled_key(const int* v2c, const int* c2v, size_t E, int n, int k, int dv, int dc) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; h ^= h >> 31; };
+    mix((uint64_t)(uint32_t)n << 32 | (uint32_t)k); mix((uint64_t)(uint32_t)dv << 32 | (uint32_t)dc);
+    const size_t step = std::max<size_t>(1, E / 32);
+    for (size_t e = 0; e < E; e += step) { mix((uint32_t)v2c[e]); mix((uint32_t)c2v[e]); }
+    mix((uint32_t)v2c[E - 1]); mix((uint32_t)c2v[E - 1]);
     return h;
 }
 
@@ -1018,21 +1298,19 @@ static int message_passing_impl(int* Mvc, int iterations, int* variable_to_check
     if (!Mvc || !variable_to_check_list || !check_to_variable_list || (!errors && iterations > 0))
         return fail(LDPC_B200_EINVAL, "message_passing: NULL argument");
     if (iterations <= 0) return 0;  // message_passing.c:15,81: loop does not run, returns it == 0
+    if (n <= 0 || dv <= 0) return fail(LDPC_B200_EINVAL, "message_passing: bad sizes n=%d dv=%d", n, dv);
     const size_t E = (size_t)n * dv;
-    uint64_t h = 1469598103934665603ull;
-    const int dims[4] = {n, k, dv, dc};
-    h = fnv1a(dims, sizeof dims, h);
-    h = fnv1a(variable_to_check_list, E * sizeof(int), h);
-    h = fnv1a(check_to_variable_list, E * sizeof(int), h);
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    const uint64_t key = sampled_key(variable_to_check_list, check_to_variable_list, E, n, k, dv, dc);
     ldpc_b200_graph* g = nullptr;
-    auto itc = g_cache.find(h);
-    if (itc != g_cache.end()) {
-        g = itc->second;
-        if (g->n != n || g->k != k || g->dv != dv || g->dc != dc ||
-            memcmp(g->v2c.data(), variable_to_check_list, E * sizeof(int)) != 0 ||
-            memcmp(g->c2v.data(), check_to_variable_list, E * sizeof(int)) != 0)
-            g = nullptr;  // hash collision: fall through to an uncached handle
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        for (auto& ce : g_cache)
+            if (ce.key == key && ce.g->n == n && ce.g->k == k && ce.g->dv == dv && ce.g->dc == dc &&
+                memcmp(ce.g->v2c.data(), variable_to_check_list, E * sizeof(int)) == 0 &&
+                memcmp(ce.g->c2v.data(), check_to_variable_list, E * sizeof(int)) == 0) {
+                g = ce.g; ce.tick = ++g_cache_tick; ce.users++;
+                break;
+            }
     }
     bool cached = g != nullptr;
     if (!g) {
@@ -1040,30 +1318,38 @@ static int message_passing_impl(int* Mvc, int iterations, int* variable_to_check
         int rc = ldpc_b200_graph_create(variable_to_check_list, check_to_variable_list, n, k, dv, dc,
                                         dev_s ? atoi(dev_s) : 0, &g);
         if (rc) return rc;
-        if (itc == g_cache.end()) {
-            if (g_cache.size() >= 64) {  // bound the cache
-                for (auto& kv : g_cache) ldpc_b200_graph_destroy(kv.second);
-                g_cache.clear();
-            }
-            g_cache[h] = g;
-            cached = true;
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (g_cache.size() >= kCacheMax) {   // drop the least recently used handle nobody is inside
+            int victim = -1;
+            for (int i = 0; i < (int)g_cache.size(); i++)
+                if (g_cache[i].users == 0 && (victim < 0 || g_cache[i].tick < g_cache[victim].tick)) victim = i;
+            if (victim >= 0) { ldpc_b200_graph_destroy(g_cache[victim].g); g_cache.erase(g_cache.begin() + victim); }
         }
+        if (g_cache.size() < kCacheMax) { g_cache.push_back({g, key, ++g_cache_tick, 1}); cached = true; }
     }
-    struct Guard { ldpc_b200_graph* g; bool keep; ~Guard() { if (!keep) ldpc_b200_graph_destroy(g); } } guard{g, cached};
+    struct Guard {
+        ldpc_b200_graph* g; bool keep;
+        ~Guard() {
+            if (!keep) { ldpc_b200_graph_destroy(g); return; }
+            std::lock_guard<std::mutex> lock(g_cache_mutex);
+            for (auto& ce : g_cache) if (ce.g == g) { ce.users--; break; }
+        }
+    } guard{g, cached};
 
-    std::vector<int8_t> frame(n);
+    static thread_local std::vector<int8_t> frame, input;
+    static thread_local std::vector<int> cnt;
+    frame.resize(n); cnt.resize(iterations);
     for (int i = 0; i < n; i++) {
         if (Mvc[i] < 0 || Mvc[i] > 2) return fail(LDPC_B200_EINVAL, "message_passing: Mvc[%d]=%d outside {0,1,2}", i, Mvc[i]);
         frame[i] = (int8_t)Mvc[i];
     }
-    std::vector<int8_t> input = frame;
-    std::vector<int> cnt(iterations);
+    bool prefilled = false;
+    for (int it = 0; it < iterations; it++) prefilled |= (errors[it] != 0);
+    if (prefilled) input = frame;
     int ret = 0;
     int rc = ldpc_b200_decode_batch(g, frame.data(), 1, iterations, cnt.data(), &ret);
     if (rc) return rc;
 
-    bool prefilled = false;
-    for (int it = 0; it < iterations; it++) prefilled |= (errors[it] != 0);
     if (!prefilled) {
         for (int it = 0; it < iterations; it++) errors[it] = cnt[it];
         for (int i = 0; i < n; i++) Mvc[i] = frame[i];

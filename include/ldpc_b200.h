@@ -164,6 +164,12 @@ int ldpc_b200_smem_probe(int device, double *gbytes_per_s);
  * wavefronts per flooding iteration of the natural / chosen / conflict-free layouts. */
 int ldpc_b200_set_place_effort(ldpc_b200_graph *g, int effort);
 int ldpc_b200_placement_info(ldpc_b200_graph *g, int words, double *natural, double *placed, double *ideal);
+/* The bank-conflict-aware placement is searched on background host threads (or read from the verified disk cache,
+ * $LDPC_B200_CACHE_DIR / ~/.cache/ldpc_b200) while the first launches already decode on the natural layout -- same
+ * results, ~1.5x slower kernels.  This call blocks until no search of the handle is running and every result is on
+ * the device (benchmarks call it before their timed region).  source (may be NULL) receives for `words` (1, 2, 4;
+ * 0 = none): 0 = no placement yet, 1 = searched in this process, 2 = read from the disk cache. */
+int ldpc_b200_placement_wait(ldpc_b200_graph *g, int words, int *source);
 
 /* Engine override: 0 automatic (shared-memory engine when the graph fits, else streamed), 1 = E1, 2 = E2. */
 int ldpc_b200_set_engine(ldpc_b200_graph *g, int engine);

@@ -34,7 +34,7 @@ class BEC:                                                    # channels.py:4-26
         return np.where(random_vector < self.erasure_prob, 2, input_binary)
 
 
-def message_pass_decode(n, k, dv, dc, binary_sequence, max_its, check_lookup, variable_lookup):
+def message_pass_decode(n, k, dv, dc, binary_sequence, max_its, check_lookup, variable_lookup, lib_path=None):
     """parallel_simulator_expurgated.py:144-167, lookups given."""
     check_lookup = np.array(check_lookup, dtype='int32').flatten()
     variable_lookup = np.array(variable_lookup, dtype='int32').flatten()
@@ -45,15 +45,18 @@ def message_pass_decode(n, k, dv, dc, binary_sequence, max_its, check_lookup, va
     check_lookup_p = check_lookup.ctypes.data_as(ct.POINTER(ct.c_int))
     variable_lookup_p = variable_lookup.ctypes.data_as(ct.POINTER(ct.c_int))
     errors_p = errors.ctypes.data_as(ct.POINTER(ct.c_int))
-    c_message_pass = ct.CDLL(base_directory + 'message_passing.so')          # :162, re-opened every frame
+    c_message_pass = ct.CDLL(lib_path or base_directory + 'message_passing.so')          # :162, re-opened every frame
     c_message_pass.message_passing(binary_sequence_p, ct.c_int(max_its), variable_lookup_p, check_lookup_p, errors_p,
                                    ct.c_int(n), ct.c_int(k), ct.c_int(dv), ct.c_int(dc))
     errors = np.insert(errors, 0, initial_error_count)
     return binary_sequence, errors
 
 
-def run_fixed_loop(n, dv, dc, erasure_prob, iterations, check_lookup, variable_lookup, seconds=5.0, max_frames=10 ** 9):
+def run_fixed_loop(n, dv, dc, erasure_prob, iterations, check_lookup, variable_lookup, seconds=5.0, max_frames=10 ** 9,
+                   lib_path=None):
     """The loop of :367-392 for `seconds` of wall clock (no 200-block-error stop: a throughput sample).
+    lib_path: the shared object the loop opens instead of the reference's message_passing.so (the
+    one-line swap to libldpc_b200.so) -- the same loop then measures the drop-in symbol.
     Returns (frames, elapsed seconds, block errors)."""
     k = int(n * (dc - dv) / dc)
     codeword = np.zeros(n)
@@ -64,7 +67,7 @@ def run_fixed_loop(n, dv, dc, erasure_prob, iterations, check_lookup, variable_l
     t0 = time.perf_counter()
     while i < max_frames and time.perf_counter() - t0 < seconds:
         channel_output = sim_BEC.new_transmit(codeword)
-        decoded, errors = message_pass_decode(n, k, dv, dc, channel_output, iterations, check_lookup, variable_lookup)
+        decoded, errors = message_pass_decode(n, k, dv, dc, channel_output, iterations, check_lookup, variable_lookup, lib_path)
         message_passing_error_counts += errors
         if errors[-1] != 0:
             block_errors += 1

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # placements found by the tests go to a scratch cache directory, not to the user's ~/.cache
+    import tempfile
+    os.environ.setdefault("LDPC_B200_CACHE_DIR", tempfile.mkdtemp(prefix="ldpc_b200_cache_"))
 
 
 @pytest.fixture(scope="session")

@@ -263,3 +263,40 @@ def test_spill_budget_follows_free_memory_and_fails_cleanly(L, oracle):
         assert "spill" in str(ei.value)
     got2 = g.mc_run(eps, seed, frames, its)
     assert np.array_equal(got2, want)
+
+
+def test_background_placement_and_disk_cache(L, oracle, tmp_path):
+    """The first launch runs while the placement search is still in the background (natural layout), later ones on the
+    placed layout: identical counters.  The finished placement is cached on disk, a new handle reads it back
+    (verified), and a corrupted file is ignored."""
+    vl, cl = L.generate_graph(3000, 3, 6, seed=5, mode=1)
+    eps, seed, frames, its = [0.40, 0.42], 3, 20000, 200
+    want = oracle.best().mc_run(vl, cl, 3000, 1500, 3, 6, eps, seed, 0, frames, its, -1, nthreads=16)
+    with _env(LDPC_B200_CACHE_DIR=str(tmp_path), LDPC_B200_CACHE=None, LDPC_B200_PLACE_SYNC=None):
+        g = L.Graph(vl, cl)
+        first, st = g.mc_run(eps, seed, frames, its, return_stats=True)      # search (0.5+ s) still running: natural layout
+        assert np.array_equal(first, want)
+        assert g.wait_placement(st["words"]) == 1                            # searched in this process
+        info = g.placement_info(st["words"])
+        assert info["gather_wavefronts_placed"] < 0.6 * info["gather_wavefronts_natural"]
+        assert np.array_equal(g.mc_run(eps, seed, frames, its), want)        # placed layout
+        files = [f for f in os.listdir(tmp_path) if f.startswith("place_")]
+        assert len(files) == 1
+        g2 = L.Graph(vl, cl)
+        assert np.array_equal(g2.mc_run(eps, seed, frames, its), want)
+        assert g2.wait_placement(st["words"]) == 2                           # read from the disk cache
+        assert g2.placement_info(st["words"]) == info
+        # a damaged cache file must not be trusted: flip lookups in place
+        path = os.path.join(tmp_path, files[0])
+        raw = bytearray(open(path, "rb").read())
+        for k in range(200, 240):
+            raw[-k] ^= 0x5A
+        open(path, "wb").write(bytes(raw))
+        g3 = L.Graph(vl, cl)
+        assert np.array_equal(g3.mc_run(eps, seed, frames, its), want)
+        assert g3.wait_placement(st["words"]) == 1                           # searched again
+        assert np.array_equal(g3.mc_run(eps, seed, frames, its), want)
+    with _env(LDPC_B200_PLACE_SYNC=1, LDPC_B200_CACHE=0):
+        g4 = L.Graph(vl, cl)
+        got, st4 = g4.mc_run(eps, seed, frames, its, return_stats=True)
+        assert np.array_equal(got, want) and g4.wait_placement(st4["words"]) == 1

@@ -1,4 +1,7 @@
-run() { timeout 300 python tools/sweep.py "$@" 2>&1 | tail -1 | sed -e 's/ place=.*overlap:/ overlap:/' -e 's/ place=.*//' | cut -c1-400; }
-export LDPC_B200_OVERLAP=0
-for cfg in "1024 8" "1024 6" "1024 4" "896 8" "896 6" "896 4" "768 8"; do set -- $cfg
-  export LDPC_B200_OV_THREADS=$1 LDPC_B200_PRODUCERS=$2; echo "c2 threads=$1 producers=$2"; run 10000 3 6 0.38,0.39,0.40,0.41,0.42,0.43 2000000; done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2d_tests.log 2>&1; tail -5 gpurun_out/r2d_tests.log
+for t in 2 0; do export LDPC_B200_E2_TMA=$t; echo "E2_TMA=$t"; python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-legs --no-cold 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']; print('c3 value %.4g EU/s %.4g frac %.3f ms/step %.1f infl %.3f'%(d['value'], d['edge_updates_per_s'], r['frac'], d['ms_per_step'], r['lane_inflation']))"; done
+unset LDPC_B200_E2_TMA
+python tools/dropin_bench.py 1000 3
+python tools/dropin_bench.py 10000 2

@@ -26,6 +26,9 @@ for cfg in cfgs:
     try:
         g.mc_launch(eps, 1, frames, cap, d.data_ptr(), st)
         torch.cuda.synchronize()
+        g.wait_placement()   # the first launch may have run on the natural layout (background placement search)
+        g.mc_launch(eps, 3, min(frames, 200000), cap, d.data_ptr(), st)
+        torch.cuda.synchronize()
         g.kernel_times_ms(); g.mc_stats()
         d.zero_()
         g.mc_launch(eps, 2, frames, cap, d.data_ptr(), st)
