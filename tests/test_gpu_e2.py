@@ -18,12 +18,21 @@ def _noisy(rng, frames, n, eps, values=True):
     return np.where(rng.random((frames, n)) < eps, 2, base).astype(np.int8)
 
 
-@pytest.fixture(scope="module")
-def g1000_e2(L):
+@pytest.fixture(scope="module", params=["plain", "tma"])
+def g1000_e2(L, request):
+    """E2 forced on a small graph, with the lookups read by plain loads (the default) and streamed per warp through the
+    TMA (cp.async.bulk + mbarrier, LDPC_B200_E2_TMA=1): every test using this fixture runs both ways."""
+    import os
     vl, cl = L.generate_graph(1000, 3, 6, seed=1, mode=1)
     g = L.Graph(vl, cl)
     g.set_engine(2)
-    return g
+    old = os.environ.get("LDPC_B200_E2_TMA")
+    os.environ["LDPC_B200_E2_TMA"] = "1" if request.param == "tma" else "2"
+    yield g
+    if old is None:
+        os.environ.pop("LDPC_B200_E2_TMA", None)
+    else:
+        os.environ["LDPC_B200_E2_TMA"] = old
 
 
 @pytest.mark.parametrize("frames,its,exp", [(1500, 200, -1), (100, 200, -1), (1024, 3, -1), (2100, 60, 0), (700, 60, 25),
