@@ -601,16 +601,8 @@ __device__ __noinline__ uint32_t bec_finish(const BecParams& bp, uint32_t point,
 // levels, no exit tests); the ~12 % of words that still have an undecided frame are appended to a queue
 // (in the `two` array, idle during the draw) and continued one block per round by whichever thread picks
 // them up: 2.15 blocks per word.  Thread-local partial results: `red` (OR per word) and `cnt` (popcount).
-// what team_draw reads of the kernel parameters (E1Params has the same members; the producer warps of the overlapped
-// stage-0 kernel, e1_overlap.cuh, pass this small copy)
-struct DrawParams {
-    int n, m;
-    const uint16_t* var_orig;
-    uint32_t seed_lo, seed_hi, draw_qcap;
-};
-
-template <int WORDS, bool MASKED, class PT = E1Params>
-__device__ __forceinline__ void team_draw(const PT& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
+template <int WORDS, bool MASKED>
+__device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
                                           unsigned long long q0, const uint32_t (&valid)[WORDS],
                                           const uint32_t (&mask)[WORDS], VecT<WORDS>* x, uint32_t* qbuf,
                                           uint32_t* qc, uint32_t (&red)[WORDS], uint32_t& cnt, uint32_t qentries = 0) {
@@ -659,7 +651,7 @@ __device__ __forceinline__ void team_draw(const PT& P, const TeamCtx& t, const B
         if (i + t.nthr < s1) var_next = P.var_orig ? (uint32_t)P.var_orig[i + t.nthr] : (uint32_t)(i + t.nthr);
         uint32_t lt[WORDS], eq[WORDS];
         LDPC_FORW {
-            bec_first8(bp, M, point, q0 + w, var, lt[w], eq[w]);
+            bec_first8_rk(M, P.rk, point, q0 + w, var, lt[w], eq[w]);
             eq[w] &= valid[w];
         }
         LDPC_FORW {
@@ -688,7 +680,7 @@ __device__ __forceinline__ void team_draw(const PT& P, const TeamCtx& t, const B
             const uint32_t i = ent.x / WORDS, w = ent.x % WORDS;
             const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : i;
             uint32_t lt = 0u, eq = ent.y;
-            bec_block(bp, point, q0 + w, var, b, lt, eq);
+            bec_block_rk(bp, P.rk, point, q0 + w, var, b, lt, eq);
             if (!bec_done_after(bp, b, eq)) {
                 const uint32_t slot = atomicAdd(&qc[b], 1u);
                 if (slot < capD) dst[slot] = make_uint2(ent.x, eq);
