@@ -32,10 +32,14 @@ constexpr int E2_COUNT_SLICE = 4080;  // variables per thread in the per-frame c
 constexpr int E2_TILE = 32;           // nodes per streamed tile of lookups (one warp's tile)
 constexpr int E2_TILE_MAXDEG = 8;     // tiles of 32 x 8 x 4 bytes = 1 KB, two per warp; larger degrees take the plain loops
 constexpr int E2_TILE_BYTES = E2_TILE * E2_TILE_MAXDEG * 4;
+constexpr int E2_TMA_SMEM = (E2_THREADS / 32) * 2 * E2_TILE_BYTES + (E2_THREADS / 32) * 2 * 8;   // tiles + mbarriers per block
 
 struct E2Params {
     const int* c2v;   // [m][dc]   (padded with zeros to a whole number of tiles when tma != 0)
     const int* v2c;   // [n][dv]
+    int async_depth;                // > 0: row gathers go through cp.async into a per-thread shared-memory ring of this
+                                    // many items (dynamic shared memory: depth * ring_width * 16 B per thread)
+    int ring_width;                 // rows per item in the ring = max(dc, dv + 1)
     int tma;                        // 1: lookups streamed as tiles through the TMA (cp.async.bulk)
     unsigned long long* tile_ctr;   // global tile work counter, zero at launch, never reset (phases use consecutive ranges)
     int n, m, dv, dc;
@@ -190,6 +194,108 @@ __device__ __forceinline__ void e2_check_node(const E2Params& P, int Q, unsigned
     }
 }
 
+// ---- asynchronous row gathers (cp.async, erasure plane only) -------------------------------------------------------
+// The plain loops keep the gathered rows of ONE node in registers (6 x 16 B per thread at dc = 6) and their round trip
+// (lookups -> rows -> combine -> store, ~2.5 us) is what bounds the phase: 1024 threads x 96 B per SM in flight.
+// Here every thread owns a ring of `depth` items in shared memory; the rows of item k+depth-1 are requested with
+// cp.async.cg (16 B each, global -> shared, no registers held, L2-coherent) before item k is combined, so `depth` times
+// as many bytes are in flight per thread.  Ring element (slot, j) of thread tid sits at ((slot*width + j)*blockDim + tid)
+// * 16: consecutive threads, consecutive 16-byte words (conflict-free LDS.128).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // n = groups that may stay pending (depth - 1, depth <= 4)
+    if (n <= 0) cp_async_wait<0>(); else if (n == 1) cp_async_wait<1>(); else if (n == 2) cp_async_wait<2>(); else cp_async_wait<3>();
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void e2_check_phase_async(const E2Params& P, unsigned long long gtid, unsigned long long gthreads, uint32_t ring) {
+    const int Q = P.R >> 2, dc = P.dc, D = P.async_depth;
+    const unsigned long long total = (unsigned long long)P.m * Q;
+    const int q = (int)(gtid % (unsigned long long)Q);   // gthreads is a multiple of Q: a thread keeps its quad column
+    const uint32_t estride = blockDim.x * 16u, sstride = (uint32_t)P.ring_width * estride;
+    auto issue = [&](unsigned long long t, int slot) {
+        const int c = (int)(t / Q);
+        const int* idx = P.c2v + (size_t)c * dc;
+        const uint32_t base = ring + (uint32_t)slot * sstride;
+        for (int j = 0; j < dc; j++) cp_async16(base + (uint32_t)j * estride, &P.X[(size_t)__ldg(idx + j) * Q + q]);
+    };
+    unsigned long long t_issue = gtid;
+    int s_issue = 0, s_use = 0;
+    for (int d = 0; d < D - 1; d++) {
+        if (t_issue < total) issue(t_issue, s_issue);
+        cp_async_commit();
+        t_issue += gthreads; s_issue = s_issue + 1 == D ? 0 : s_issue + 1;
+    }
+    for (unsigned long long t = gtid; t < total; t += gthreads) {
+        if (t_issue < total) issue(t_issue, s_issue);
+        cp_async_commit();
+        t_issue += gthreads; s_issue = s_issue + 1 == D ? 0 : s_issue + 1;
+        cp_async_wait_dyn(D - 1);
+        uint4 one = make_uint4(0, 0, 0, 0), two = one;
+        const uint32_t base = ring + (uint32_t)s_use * sstride;
+        for (int j = 0; j < dc; j++) {
+            const uint4 w = lds128(base + (uint32_t)j * estride);
+            two.x |= one.x & w.x; two.y |= one.y & w.y; two.z |= one.z & w.z; two.w |= one.w & w.w;
+            one.x |= w.x; one.y |= w.y; one.z |= w.z; one.w |= w.w;
+        }
+        P.T[t] = two;
+        s_use = s_use + 1 == D ? 0 : s_use + 1;
+    }
+    cp_async_wait<0>();
+}
+
+__device__ __forceinline__ void e2_var_phase_async(const E2Params& P, unsigned long long gtid, unsigned long long gthreads, uint32_t ring,
+                                                   const uint32_t* s_mask, uint32_t* s_or, uint32_t* s_cnt, uint32_t* g_acc) {
+    const int Q = P.R >> 2, dv = P.dv, D = P.async_depth;
+    const unsigned long long total = (unsigned long long)P.n * Q;
+    const int q = (int)(gtid % (unsigned long long)Q);
+    const uint32_t estride = blockDim.x * 16u, sstride = (uint32_t)P.ring_width * estride;
+    uint4 any = make_uint4(0, 0, 0, 0), chg = any;
+    uint32_t cnt = 0;
+    auto issue = [&](unsigned long long t, int slot) {   // element 0: the variable's own row, 1..dv: its checks' rows
+        const int i = (int)(t / Q);
+        const int* idx = P.v2c + (size_t)i * dv;
+        const uint32_t base = ring + (uint32_t)slot * sstride;
+        cp_async16(base, &P.X[t]);
+        for (int j = 0; j < dv; j++) cp_async16(base + (uint32_t)(j + 1) * estride, &P.T[(size_t)__ldg(idx + j) * Q + q]);
+    };
+    unsigned long long t_issue = gtid;
+    int s_issue = 0, s_use = 0;
+    for (int d = 0; d < D - 1; d++) {
+        if (t_issue < total) issue(t_issue, s_issue);
+        cp_async_commit();
+        t_issue += gthreads; s_issue = s_issue + 1 == D ? 0 : s_issue + 1;
+    }
+    for (unsigned long long t = gtid; t < total; t += gthreads) {
+        if (t_issue < total) issue(t_issue, s_issue);
+        cp_async_commit();
+        t_issue += gthreads; s_issue = s_issue + 1 == D ? 0 : s_issue + 1;
+        cp_async_wait_dyn(D - 1);
+        const uint32_t base = ring + (uint32_t)s_use * sstride;
+        const uint4 xi = lds128(base);
+        uint4 xn = xi;
+        for (int j = 0; j < dv; j++) {
+            const uint4 tw = lds128(base + (uint32_t)(j + 1) * estride);
+            xn.x &= tw.x; xn.y &= tw.y; xn.z &= tw.z; xn.w &= tw.w;
+        }
+        if (xn.x != xi.x || xn.y != xi.y || xn.z != xi.z || xn.w != xi.w) P.X[t] = xn;
+        any.x |= xn.x; any.y |= xn.y; any.z |= xn.z; any.w |= xn.w;
+        chg.x |= xi.x ^ xn.x; chg.y |= xi.y ^ xn.y; chg.z |= xi.z ^ xn.z; chg.w |= xi.w ^ xn.w;
+        cnt += __popc(xn.x & s_mask[q * 4]) + __popc(xn.y & s_mask[q * 4 + 1]) + __popc(xn.z & s_mask[q * 4 + 2]) +
+               __popc(xn.w & s_mask[q * 4 + 3]);
+        s_use = s_use + 1 == D ? 0 : s_use + 1;
+    }
+    cp_async_wait<0>();
+    e2_block_accumulate(s_or, s_cnt, g_acc, P.R, q, any, chg, cnt);
+}
+
 template <bool VALUES>
 __device__ __forceinline__ void e2_check_phase(const E2Params& P, unsigned long long gtid, unsigned long long gthreads, E2Stream& st) {
     const int Q = P.R >> 2;
@@ -316,20 +422,23 @@ __global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant
     __shared__ uint32_t s_valid[E2_RMAX];
     __shared__ uint32_t s_any[E2_RMAX];
     __shared__ uint32_t s_flag;
-    __shared__ __align__(128) int s_tile[E2_THREADS / 32][2][E2_TILE_BYTES / 4];
-    __shared__ __align__(8) uint64_t s_bar[E2_THREADS / 32][2];
+    // dynamic shared memory: the cp.async ring (async_depth > 0) OR the per-warp lookup tiles + mbarriers (tma)
+    extern __shared__ __align__(128) unsigned char e2_dyn[];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(e2_dyn) + threadIdx.x * 16u;
     E2Stream st;
-    {
+    st.parity[0] = 0u; st.parity[1] = 0u; st.base = 0ull;
+    st.buf[0] = st.buf[1] = nullptr; st.bar = nullptr;
+    if (P.tma) {
         const int wb = (int)threadIdx.x >> 5;
-        st.buf[0] = s_tile[wb][0]; st.buf[1] = s_tile[wb][1]; st.bar = s_bar[wb];
-        st.parity[0] = 0u; st.parity[1] = 0u; st.base = 0ull;
+        int* tiles = reinterpret_cast<int*>(e2_dyn);
+        st.buf[0] = tiles + (size_t)(wb * 2) * (E2_TILE_BYTES / 4); st.buf[1] = st.buf[0] + E2_TILE_BYTES / 4;
+        st.bar = reinterpret_cast<uint64_t*>(e2_dyn + (size_t)(E2_THREADS / 32) * 2 * E2_TILE_BYTES) + wb * 2;
         if ((threadIdx.x & 31) == 0) {
             mbar_init(&st.bar[0], 1u); mbar_init(&st.bar[1], 1u);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
     }
-
     const int R = P.R, Q = R >> 2;
     const int ACC = 2 * E2_RMAX + 1;
     const unsigned long long gthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -416,10 +525,12 @@ __global__ void __launch_bounds__(E2_THREADS, 4) e2_kernel(const __grid_constant
                 if (pass == 0) for (int w = 0; w < R; w++) exec_sum += __popc(s_running[w]);
                 if (DECODE && blockIdx.x == 0)   // only block 0 reads framecnt, and it is past those reads
                     for (int f = threadIdx.x; f < 32 * E2_RMAX; f += blockDim.x) P.framecnt[f] = 0;
-                e2_check_phase<VALUES>(P, gtid, gthreads, st);
+                if (!VALUES && P.async_depth > 0) e2_check_phase_async(P, gtid, gthreads, ring);
+                else e2_check_phase<VALUES>(P, gtid, gthreads, st);
                 zero_block_acc();
                 grid.sync();
-                e2_var_phase<VALUES>(P, gtid, gthreads, s_mask, s_or, &s_cnt, P.acc + par * ACC, st);
+                if (!VALUES && P.async_depth > 0) e2_var_phase_async(P, gtid, gthreads, ring, s_mask, s_or, &s_cnt, P.acc + par * ACC);
+                else e2_var_phase<VALUES>(P, gtid, gthreads, s_mask, s_or, &s_cnt, P.acc + par * ACC, st);
                 zero_global_acc(par ^ 1);   // everyone finished reading it before the sync above
                 grid.sync();
                 if (DECODE) {

@@ -36,8 +36,8 @@ while time.time() - t0 < budget:
     thr = 1 - (1 - 1.0 / (dc - 1)) if dv == 2 else 0.45       # rough scale of interesting eps
     eps = [float(np.clip(rng.normal(0.8 * thr, 0.15), 0.0, 1.0)) for _ in range(npts)]
     frames = int(rng.choice([1, 31, 32, 33, 127, 128, 129, 500, 1000, 2500]))
-    if rng.random() < 0.15:
-        frames = int(rng.integers(33000, 36000))            # long enough for the staged path
+    if rng.random() < (0.4 if (dv, dc) in ((3, 6), (4, 8)) else 0.15):
+        frames = int(rng.integers(33000, 36000))            # long enough for the staged path (and the overlapped stage 0)
     if n * frames * max(its, 1) > 6e9:
         frames = max(1, int(6e9 / (n * max(its, 1))))
     exp = int(rng.choice([-1, -1, 0, 1, n // 20, n]))
@@ -45,7 +45,17 @@ while time.time() - t0 < budget:
     words = int(rng.choice([0, 1, 2, 4]))
     first = int(rng.integers(0, 50)) * 128
     seed = int(rng.integers(1 << 62))
-    desc = f"n={n} ({dv},{dc}) its={its} eps={np.round(eps, 3).tolist()} frames={frames} exp={exp} engine={engine} words={words} first={first}"
+    # round-2 paths, switched per case: overlapped stage 0 (auto / forced / off) with 1..8 producer warps, socket lists in
+    # tensor or shared memory, E2 lookups through the TMA or plain loads, two-pass expurgation forced, blocking or
+    # background placement search
+    knobs = {"LDPC_B200_OVERLAP": int(rng.choice([0, 1, 1, 2])), "LDPC_B200_PRODUCERS": int(rng.choice([1, 2, 3, 4, 8])),
+             "LDPC_B200_TMEM": int(rng.choice([0, 0, 2])), "LDPC_B200_E2_TMA": int(rng.choice([1, 2])),
+             "LDPC_B200_EXP2PASS": int(rng.choice([0, 1])), "LDPC_B200_PLACE_SYNC": int(rng.choice([0, 1])),
+             "LDPC_B200_CACHE": 0}
+    for k_, v_ in knobs.items():
+        os.environ[k_] = str(v_)
+    desc = (f"n={n} ({dv},{dc}) its={its} eps={np.round(eps, 3).tolist()} frames={frames} exp={exp} engine={engine} words={words} "
+            f"first={first} knobs={knobs}")
     try:
         g = L.Graph(vl, cl)
         g.set_engine(engine)
