@@ -1,5 +1,5 @@
-// e1_overlap.cuh -- stage 0 of the staged E1 Monte-Carlo pipeline with the channel draw OVERLAPPED with the decoding
-// (warp-specialised producer / consumer CTA).
+// e1_overlap.cuh -- the staged E1 Monte-Carlo pipeline with the channel draw (stage 0) and the survivor reload (later
+// stages) OVERLAPPED with the decoding (warp-specialised producer / consumer CTA).
 //
 // Why: in the staged kernel (e1_staged.cuh) a team first draws its group's erasure pattern (channels.py:24-26;
 // Philox + bit-sliced comparison: ALU work only, the shared-memory pipe idles) and then decodes it
@@ -164,7 +164,10 @@ __device__ __forceinline__ void ov_producer_loop(const E1Params& P, const StageP
     t.lane = threadIdx.x & 31;
     t.warp = t.tid >> 5;
     const int all = (NC + NP) * 32;
-    const unsigned long long total = (unsigned long long)P.npoints * P.groups_per_point;
+    constexpr int W = 32 * WORDS;
+    unsigned long long total = 0;   // stage 0: every group of every point; later stages: dense groups of the spilled survivors
+    if (S.stage == 0) total = (unsigned long long)P.npoints * P.groups_per_point;
+    else for (int p = 0; p < P.npoints; p++) total += (S.cnt_in[p] + W - 1) / W;
     t.bar_id = OV_BAR_PROD;
     t.sm = smem; t.sa_x = 0; t.sa_t = 0; t.ta_c = 0; t.ta_v = 0;
     t.scr = reinterpret_cast<uint32_t*>(smem + P.sm_pscr);
@@ -192,19 +195,40 @@ __device__ __forceinline__ void ov_producer_loop(const E1Params& P, const StageP
             ov_bar_arrive(OV_BAR_FULL, all);
             break;
         }
-        const uint32_t point = (uint32_t)(item / P.groups_per_point);
-        const unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
-        uint32_t valid[WORDS];
-        LDPC_FORW {
-            const unsigned long long f0 = (gi * WORDS + w) * 32ull;
-            valid[w] = f0 >= P.num_frames ? 0u
-                       : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+        uint32_t point;
+        unsigned long long gi;
+        uint32_t valid[WORDS], red[WORDS], cnt = 0u;
+        if (S.stage == 0) {
+            point = (uint32_t)(item / P.groups_per_point);
+            gi = item - (unsigned long long)point * P.groups_per_point;
+            LDPC_FORW {
+                const unsigned long long f0 = (gi * WORDS + w) * 32ull;
+                valid[w] = f0 >= P.num_frames ? 0u
+                           : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+            }
+            const BecParams bp = P.bec[point];
+            warp_draw<WORDS>(P, t.lane, t.warp, NP, bp, point + P.point0, P.first_word + gi * WORDS, valid, stg,
+                             smem + P.sm_q + (uint32_t)t.warp * ov_wq_bytes(), red, cnt);
+        } else {
+            // later stages: the producers RELOAD the next dense group of survivors (frame-major records -> bit-sliced
+            // state through 32x32 transposes) while the consumers decode the current one
+            unsigned long long rest = item;
+            int p = 0;
+            for (; p < P.npoints; p++) {
+                const unsigned long long gp = (S.cnt_in[p] + W - 1) / W;
+                if (rest < gp) break;
+                rest -= gp;
+            }
+            point = (uint32_t)p; gi = rest;
+            const unsigned long long left = S.cnt_in[p] - gi * W;
+            LDPC_FORW {
+                const unsigned long long f0 = (unsigned long long)w * 32ull;
+                valid[w] = f0 >= left ? 0u : (left - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(left - f0)) - 1u));
+                red[w] = valid[w];
+            }
+            stage_reload_group<WORDS>(P, S, t, stg, point, gi, valid);
         }
-        const BecParams bp = P.bec[point];
-        uint32_t red[WORDS], cnt;
-        warp_draw<WORDS>(P, t.lane, t.warp, NP, bp, point + P.point0, P.first_word + gi * WORDS, valid, stg,
-                         smem + P.sm_q + (uint32_t)t.warp * ov_wq_bytes(), red, cnt);
-        team_reduce<WORDS>(t, red, cnt);
+        team_reduce<WORDS>(t, red, cnt);   // its barrier also completes the producers' pattern writes
         if (t.tid == 0) {
             mbox[0] = 0u; mbox[1] = point; mbox[2] = (uint32_t)gi; mbox[3] = (uint32_t)(gi >> 32); mbox[4] = cnt;
             LDPC_FORW mbox[5 + w] = red[w];
@@ -224,7 +248,7 @@ __host__ __device__ constexpr int ov_threads(int words) { return words == 2 ? 89
 
 template <int WORDS, int DV, int DC, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-e1_mc_stage0_overlap_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
+e1_mc_overlap_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t tm_slot;
     constexpr int W = 32 * WORDS;
@@ -278,18 +302,27 @@ e1_mc_stage0_overlap_kernel(const __grid_constant__ E1Params P, const __grid_con
             uint32_t any[WORDS], valid[WORDS];
             LDPC_FORW {
                 any[w] = mbox[5 + w];
-                const unsigned long long f0 = (gi * WORDS + w) * 32ull;
-                valid[w] = f0 >= P.num_frames ? 0u
-                           : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+                if (S.stage == 0) {
+                    const unsigned long long f0 = (gi * WORDS + w) * 32ull;
+                    valid[w] = f0 >= P.num_frames ? 0u
+                               : (P.num_frames - f0 >= 32ull ? 0xFFFFFFFFu : ((1u << (uint32_t)(P.num_frames - f0)) - 1u));
+                } else valid[w] = any[w];   // survivors: all of them still hold erasures
             }
             for (int i = t.tid; i < nvec4; i += t.nthr) x4[i] = s4[i];
             ov_bar_arrive(OV_BAR_EMPTY, all);   // this thread's part of the pattern and the mailbox are taken
-            if (S.exp_mode)
-                for (int f = t.tid; f < W; f += t.nthr) fid[f] = (uint32_t)(gi * W + f);
+            if (S.exp_mode) {
+                if (S.stage == 0) {
+                    for (int f = t.tid; f < W; f += t.nthr) fid[f] = (uint32_t)(gi * W + f);
+                } else {   // the frame id travels in the last word of the spill record
+                    const uint32_t* recs = S.spill_in + ((size_t)point * S.point_stride + gi * W) * S.rec_words;
+                    for (int f = t.tid; f < W; f += t.nthr)
+                        fid[f] = (unsigned long long)f < S.cnt_in[point] - gi * W ? recs[(size_t)f * S.rec_words + S.rec_words - 1] : 0u;
+                }
+            }
             if (t.tid == 0) hbuf[0] = cnt;
             team_sync(t);   // x complete
 
-            const int lo = S.cuts[point * nst1], hi = S.cuts[point * nst1 + 1];
+            const int lo = S.cuts[point * nst1 + S.stage], hi = S.cuts[point * nst1 + S.stage + 1];
             uint32_t running[WORDS];
             LDPC_FORW running[w] = valid[w];
             unsigned long long exec_sum = 0;

@@ -178,6 +178,34 @@ __device__ __forceinline__ void stage_finish_group(const E1Params& P, const Stag
     }
 }
 
+// Reload of one dense group of survivors: frame-major spill records of `point`, records [gi*W, gi*W + W), back into the
+// bit-sliced state `x` (32x32 bit transposes).  Team-cooperative (every warp of `t` takes slices of the record).
+// Shared by the staged kernel and the producers of the overlapped kernel (e1_overlap.cuh).
+template <int WORDS>
+__device__ __forceinline__ void stage_reload_group(const E1Params& P, const StageParams& S, const TeamCtx& t, VecT<WORDS>* x,
+                                                   uint32_t point, unsigned long long gi, const uint32_t (&valid)[WORDS]) {
+    constexpr int W = 32 * WORDS;
+    const uint32_t* recs = S.spill_in + ((size_t)point * S.point_stride + gi * W) * S.rec_words;
+    for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
+        VecT<WORDS> o[4];   // state vectors of variables s0, s0+32, s0+64, s0+96: whole-vector stores (no bank conflicts)
+        LDPC_FORW {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if ((valid[w] >> t.lane) & 1u)
+                r = *reinterpret_cast<const uint4*>(recs + (size_t)(w * 32 + t.lane) * S.rec_words + j0);
+            if (valid[w] != 0u) {   // team-uniform
+                o[0].a[w] = transpose32(r.x, t.lane); o[1].a[w] = transpose32(r.y, t.lane);
+                o[2].a[w] = transpose32(r.z, t.lane); o[3].a[w] = transpose32(r.w, t.lane);
+            } else {
+                o[0].a[w] = 0u; o[1].a[w] = 0u; o[2].a[w] = 0u; o[3].a[w] = 0u;
+            }
+        }
+        const int s0 = 32 * j0 + t.lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (s0 + 32 * k < P.n) x[s0 + 32 * k] = o[k];
+    }
+}
+
 template <int WORDS, int DV, int DC, bool TM = false>
 __global__ void __launch_bounds__(e1_threads(WORDS), 1)
 e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ StageParams S) {
@@ -294,24 +322,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             if (S.exp_mode)
                 for (int f = t.tid; f < W; f += t.nthr)
                     fid[f] = (unsigned long long)f < S.cnt_in[point] - gi * W ? recs[(size_t)f * S.rec_words + S.rec_words - 1] : 0u;
-            for (int j0 = t.warp * 4; j0 < S.rec_words; j0 += t.team_warps * 4) {
-                VecT<WORDS> o[4];   // state vectors of variables s0, s0+32, s0+64, s0+96: whole-vector stores (no bank conflicts)
-                LDPC_FORW {
-                    uint4 r = make_uint4(0, 0, 0, 0);
-                    if ((valid[w] >> t.lane) & 1u)
-                        r = *reinterpret_cast<const uint4*>(recs + (size_t)(w * 32 + t.lane) * S.rec_words + j0);
-                    if (valid[w] != 0u) {   // team-uniform
-                        o[0].a[w] = transpose32(r.x, t.lane); o[1].a[w] = transpose32(r.y, t.lane);
-                        o[2].a[w] = transpose32(r.z, t.lane); o[3].a[w] = transpose32(r.w, t.lane);
-                    } else {
-                        o[0].a[w] = 0u; o[1].a[w] = 0u; o[2].a[w] = 0u; o[3].a[w] = 0u;
-                    }
-                }
-                const int s0 = 32 * j0 + t.lane;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (s0 + 32 * k < P.n) x[s0 + 32 * k] = o[k];
-            }
+            stage_reload_group<WORDS>(P, S, t, x, point, gi, valid);
             LDPC_FORW any[w] = valid[w];
             team_sync(t);
         }

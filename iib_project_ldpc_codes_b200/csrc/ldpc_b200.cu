@@ -807,7 +807,9 @@ static DevPool g_dev_pool;
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) g_dev_pool.put(p, bytes); }
+    // the device is idle before a buffer goes back to the pool: on an error path work on the caller's stream may still
+    // be using it (on the normal paths the callers have synchronised already, so this costs nothing)
+    ~DevBuf() { if (p) { cudaDeviceSynchronize(); g_dev_pool.put(p, bytes); } }
     cudaError_t alloc(size_t want) { return g_dev_pool.get(want ? want : 1, &p, &bytes); }
 };
 
