@@ -98,7 +98,7 @@ struct E1Params {
     // overlapped stage 0 (e1_overlap.cuh): warps [0, team_warps) decode, warps [team_warps, team_warps + ov_np) draw the
     // next group's erasure pattern into a staging buffer meanwhile
     int ov_np;                              // producer (channel) warps; 0 = not the overlapped kernel
-    uint32_t sm_stage, sm_q, sm_pscr, sm_mbox, ov_qentries;   // staging pattern | draw queue | producer scratch | mailbox
+    uint32_t sm_stage, sm_q, sm_pscr, sm_mbox;   // staging pattern | producers' private draw queues | producer scratch | mailbox
     // ensemble mode (parallel_simulator_expurgated.py:200-223: a fresh random graph per frame): one graph
     // per `ens_gpg` frame groups, each team stages the graph of its work item into its own region
     // (sm_c2v / sm_v2c are then relative to the team base); graph g lives at c2v + g*ens_stride_c

@@ -81,7 +81,7 @@ struct E1Config {
     int v2c_res = 0; uint32_t sm_vres = 0;   // v2c_global: resident part of the variable-side lists
     bool tm = false; int tm_cpw = 0, tm_trips_c = 0, tm_trips_v = 0;   // socket lists in tensor memory (e1_tmem.cuh)
     // overlapped stage 0 (e1_overlap.cuh): team_warps consumer warps + ov_np producer warps
-    int ov_np = 0; uint32_t sm_stage = 0, sm_q = 0, sm_pscr = 0, sm_mbox = 0, ov_qentries = 0;
+    int ov_np = 0; uint32_t sm_stage = 0, sm_q = 0, sm_pscr = 0, sm_mbox = 0;
 };
 
 struct StagePlan {
@@ -247,7 +247,6 @@ static bool plan_e1_overlap(const ldpc_b200_graph* g, int cap, const E1Config& b
     c.sm_pscr = off; off += align_up((uint32_t)e1_scr_words(words) * 4, 16);
     c.sm_mbox = off; off += 64;
     c.sm_q = off; off += (uint32_t)np * ov_wq_bytes();   // one private draw queue per producer warp
-    c.ov_qentries = OV_WQ;
     if (off > limit) return false;
     // consumer warps: as many as the thread budget and the tensor-memory columns allow
     int nc = 0;
@@ -349,7 +348,7 @@ static void set_geometry(const ldpc_b200_graph* g, const E1Config& c, E1Params& 
     P.sm_x = c.sm_x; P.sm_t = c.sm_t; P.sm_v = c.sm_v; P.sm_p = c.sm_p; P.sm_hbuf = c.sm_hbuf; P.sm_scr = c.sm_scr;
     P.tm = c.tm ? 1 : 0; P.tm_cpw = c.tm_cpw; P.tm_trips_c = c.tm_trips_c; P.tm_trips_v = c.tm_trips_v;
     P.tm_full_c = g->m / (c.team_warps * 32); P.tm_full_v = g->n / (c.team_warps * 32);
-    P.ov_np = c.ov_np; P.sm_stage = c.sm_stage; P.sm_q = c.sm_q; P.sm_pscr = c.sm_pscr; P.sm_mbox = c.sm_mbox; P.ov_qentries = c.ov_qentries;
+    P.ov_np = c.ov_np; P.sm_stage = c.sm_stage; P.sm_q = c.sm_q; P.sm_pscr = c.sm_pscr; P.sm_mbox = c.sm_mbox;
 }
 
 static void fill_params(const ldpc_b200_graph* g, const E1Config& c, int cap, E1Params& P) {

@@ -1,4 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_staged.py tests/test_gpu_fuzz.py -x -q > gpurun_out/ov_tests.log 2>&1; tail -4 gpurun_out/ov_tests.log
-run() { timeout 300 python tools/sweep.py "$@" 2>&1 | tail -1 | sed -e 's/ place=.*overlap:/ overlap:/' -e 's/ place=.*//' | cut -c1-400; }
-for l in 2 0; do export LDPC_B200_OVERLAP_LATER=$l; echo "c2 overlap_later=$l"; run 10000 3 6 0.38,0.39,0.40,0.41,0.42,0.43 2000000; run 10000 3 6 0.38,0.39,0.40,0.41,0.42,0.43 2000000; done
-for l in 2 0; do export LDPC_B200_OVERLAP_LATER=$l; echo "n=8000 overlap_later=$l"; run 8000 3 6 0.38,0.40,0.42 3000000; done
+timeout 600 python tools/ens_bench2.py 2>&1 | head -8
+ncu --set full --clock-control none --import-source on -k regex:e1_mc_kernel --launch-skip 1 -c 1 -f -o gpurun_out/prof_ens python tools/ens_bench2.py > gpurun_out/ncu_ens.log 2>&1
+python tools/ncu_summary.py gpurun_out/prof_ens.ncu-rep 12 > gpurun_out/r2i_ens_ncu_full.txt 2>&1
+python tools/ncu_regions.py gpurun_out/prof_ens.ncu-rep >> gpurun_out/r2i_ens_ncu_full.txt 2>&1
+rm -f gpurun_out/prof_ens.ncu-rep
+grep -A22 "regions by" gpurun_out/r2i_ens_ncu_full.txt

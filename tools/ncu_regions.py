@@ -21,7 +21,7 @@ STALLS = ["stall_barrier", "stall_branch_resolving", "stall_dispatch", "stall_lg
           "stall_no_inst", "stall_not_selected", "stall_selected", "stall_short_sb", "stall_wait", "stall_sleep", "stall_membar"]
 REGIONS = ["team_draw", "team_draw_lanes", "warp_draw", "ov_producer_loop", "check_phase_tm", "var_phase_tm", "check_phase", "var_phase", "mc_var_phase",
            "team_reduce", "stage_finish_group", "tm_fill_lists", "team_generate_graph", "stage_v2c_resident", "reload_group",
-           "e2_check_phase", "e2_var_phase"]
+           "e2_check_phase_async", "e2_var_phase_async", "e2_check_phase", "e2_var_phase", "e2_count_phase", "stage_reload_group", "mc_group"]
 
 
 def functions_of(path, cache={}):
@@ -38,11 +38,11 @@ def functions_of(path, cache={}):
     for ln, text in enumerate(src, 1):
         code = re.sub(r"//.*", "", text)
         if depth <= 1:
-            m = re.search(r"\b([A-Za-z_]\w*)\s*\([^;]*$", code)
-            if m and not code.lstrip().startswith(("if", "for", "while", "switch", "return", "#", "else")) and \
-                    m.group(1) not in ("if", "for", "while", "switch", "__launch_bounds__", "defined", "alignas", "asm") and \
+            skip = ("if", "for", "while", "switch", "__launch_bounds__", "defined", "alignas", "asm", "e1_threads", "ov_threads")
+            names = [nm for nm in re.findall(r"\b([A-Za-z_]\w*)\s*\(", code) if nm not in skip]
+            if names and ";" not in code and not code.lstrip().startswith(("if", "for", "while", "switch", "return", "#", "else")) and \
                     pending is None and cur is None:
-                pending = m.group(1)
+                pending = names[0]
         opens, closes = code.count("{"), code.count("}")
         if pending and opens and cur is None and depth <= 1 and "namespace" not in code:
             cur, cur_depth = pending, depth
