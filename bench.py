@@ -352,10 +352,14 @@ def measure_fixed(E, name, wl, steps, warmup, with_cpu, cold=True):
                 "traffic_note": ("DRAM bytes per step of the staged pipeline = spill records written + read back between stages "
                                  "(spilled_records x record_bytes x 2, exact, from the kernels' own counters; ncu "
                                  "dram__bytes of the stage-0 launch in profiles/ agrees); graph and state never leave the SM")
-                if is_e1 else "see profiles/ (ncu dram__bytes of the E2 launch)",
+                if is_e1 else ("null here: not counted live.  ncu of the final build (profiles/r2f_e2_c3_n1e6_ncu_full.txt): 3.3 TB/s of DRAM "
+                               "traffic, about half the algorithmic bytes -- the 126 MB L2 serves the rest, so frac is against the HBM "
+                               "copy peak but the kernel is L2-assisted and can exceed 1"),
                 "peak_detail": sp if is_e1 else {"hbm_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
-                "kernel": (("e1_mc_staged_kernel x%d stages (survivor re-packing), timed as one pipeline" % stats["stages"])
-                           if stats["stages"] > 1 else "e1_mc_kernel") if is_e1 else "e2_kernel",
+                "kernel": ((("e1_mc_overlap_kernel (producer/consumer warps: draw and survivor reload overlapped with decoding)"
+                             if stats.get("overlap_producers") else "e1_mc_staged_kernel")
+                            + " x%d stages (survivor re-packing), timed as one pipeline" % stats["stages"])
+                           if stats["stages"] > 1 else "e1_mc_kernel") if is_e1 else "e2_kernel (cp.async row-gather ring)",
                 "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms * steps / ms,
                 "alg_bytes_per_edge_update": b_alg, "alg_bytes_per_launch": alg_bytes_per_launch,
                 "frac_of_hbm_peak": achieved / hbm_peak,

@@ -601,7 +601,12 @@ __device__ __noinline__ uint32_t bec_finish(const BecParams& bp, uint32_t point,
 // levels, no exit tests); the ~12 % of words that still have an undecided frame are appended to a queue
 // (in the `two` array, idle during the draw) and continued one block per round by whichever thread picks
 // them up: 2.15 blocks per word.  Thread-local partial results: `red` (OR per word) and `cnt` (popcount).
-template <int WORDS, bool MASKED>
+// CHUNK = words of a variable whose Philox chains run side by side (2 * CHUNK independent chains): all of them where the
+// registers allow, one at a time in the kernels that keep the socket lists in shared memory (the ensemble kernel at
+// W = 128 lost 13 % to spills with four)
+// RK: round keys read from the kernel parameters (E1Params::rk) instead of derived from the seed in the loop -- a win where
+// the chains are interleaved (tensor-memory kernels), a loss in the register-bound ensemble kernel (1.34 -> 0.83e8 frames/s)
+template <int WORDS, bool MASKED, int CHUNK = WORDS, bool RK = true>
 __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, const BecParams& bp_, uint32_t point,
                                           unsigned long long q0, const uint32_t (&valid)[WORDS],
                                           const uint32_t (&mask)[WORDS], VecT<WORDS>* x, uint32_t* qbuf,
@@ -649,20 +654,27 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
         VecT<WORDS> xi;
         uint32_t var_next = 0u;
         if (i + t.nthr < s1) var_next = P.var_orig ? (uint32_t)P.var_orig[i + t.nthr] : (uint32_t)(i + t.nthr);
-        uint32_t lt[WORDS], eq[WORDS];
-        LDPC_FORW {
-            bec_first8_rk(M, P.rk, point, q0 + w, var, lt[w], eq[w]);
-            eq[w] &= valid[w];
-        }
-        LDPC_FORW {
-            if (eq[w] != 0u && deeper) {
-                const uint32_t slot = atomicAdd(&qc[1], 1u);
-                if (slot < capA) qA[slot] = make_uint2((uint32_t)i * WORDS + w, eq[w]);
-                else lt[w] |= bec_finish(bp, point, q0 + w, var, 2, eq[w]);
+#pragma unroll
+        for (int w0 = 0; w0 < WORDS; w0 += CHUNK) {
+            uint32_t lt[CHUNK], eq[CHUNK];
+#pragma unroll
+            for (int c = 0; c < CHUNK; c++) {
+                if (RK) bec_first8_rk(M, P.rk, point, q0 + w0 + c, var, lt[c], eq[c]);
+                else bec_first8(bp, M, point, q0 + w0 + c, var, lt[c], eq[c]);
+                eq[c] &= valid[w0 + c];
             }
-            xi.a[w] = lt[w] & valid[w];
-            red[w] |= xi.a[w];
-            cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
+#pragma unroll
+            for (int c = 0; c < CHUNK; c++) {
+                const int w = w0 + c;
+                if (eq[c] != 0u && deeper) {
+                    const uint32_t slot = atomicAdd(&qc[1], 1u);
+                    if (slot < capA) qA[slot] = make_uint2((uint32_t)i * WORDS + w, eq[c]);
+                    else lt[c] |= bec_finish(bp, point, q0 + w, var, 2, eq[c]);
+                }
+                xi.a[w] = lt[c] & valid[w];
+                red[w] |= xi.a[w];
+                cnt += __popc(MASKED ? (xi.a[w] & mask[w]) : xi.a[w]);
+            }
         }
         x[i] = xi;
         var = var_next;
@@ -680,7 +692,8 @@ __device__ __forceinline__ void team_draw(const E1Params& P, const TeamCtx& t, c
             const uint32_t i = ent.x / WORDS, w = ent.x % WORDS;
             const uint32_t var = P.var_orig ? (uint32_t)P.var_orig[i] : i;
             uint32_t lt = 0u, eq = ent.y;
-            bec_block_rk(bp, P.rk, point, q0 + w, var, b, lt, eq);
+            if (RK) bec_block_rk(bp, P.rk, point, q0 + w, var, b, lt, eq);
+            else bec_block(bp, point, q0 + w, var, b, lt, eq);
             if (!bec_done_after(bp, b, eq)) {
                 const uint32_t slot = atomicAdd(&qc[b], 1u);
                 if (slot < capD) dst[slot] = make_uint2(ent.x, eq);
@@ -771,7 +784,7 @@ __device__ __forceinline__ int mc_group(const E1Params& P, const TeamCtx& t, con
     if (P.recount)
         team_draw_lanes<WORDS, MASKED>(P, t, bp, point + P.point0, t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS + 8, valid, mask, x, red, cnt);
     else
-        team_draw<WORDS, MASKED>(P, t, bp, point + P.point0, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
+        team_draw<WORDS, MASKED, TM ? WORDS : 1, TM>(P, t, bp, point + P.point0, q0, valid, mask, x, reinterpret_cast<uint32_t*>(two),
                                  t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
     team_reduce<WORDS>(t, red, cnt);
     LDPC_FORW any[w] = red[w];

@@ -310,7 +310,7 @@ e1_mc_staged_kernel(const __grid_constant__ E1Params P, const __grid_constant__ 
             const BecParams bp = P.bec[point];
             const unsigned long long q0 = P.first_word + gi * WORDS;
             uint32_t red[WORDS];
-            team_draw<WORDS, false>(P, t, bp, point + P.point0, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
+            team_draw<WORDS, false, TM ? WORDS : 1, TM>(P, t, bp, point + P.point0, q0, valid, valid, x, reinterpret_cast<uint32_t*>(two),
                                     t.scr + 32 * (2 * WORDS + 1) + 2 + 32 * WORDS, red, cnt);
             if (S.exp_mode)
                 for (int f = t.tid; f < W; f += t.nthr) fid[f] = (uint32_t)(gi * W + f);

@@ -17,6 +17,7 @@
 #include <new>
 #include <exception>
 #include <thread>
+#include <chrono>
 #include <memory>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -123,6 +124,7 @@ struct ldpc_b200_graph {
         std::unique_ptr<Placement> result;
     } placed[5];
     uint64_t graph_hash = 0;           // content hash (dims + lookups), keys the placement cache on disk
+    cudaEvent_t chunk_ev[2] = {nullptr, nullptr};   // throttle of the chunk loop while a placement search is pending
     int place_effort = -1;  // -1: LDPC_B200_PLACE_EFFORT or default
     // E2 (HBM/L2-streamed engine): int32 lookups in the reference layouts + frame-minor state rows
     int* d_c2v32 = nullptr; int* d_v2c32 = nullptr;
@@ -166,6 +168,11 @@ struct ldpc_b200_graph {
     int ev_count = 0;
     bool ev_init = false;
 };
+
+static double host_seconds() {   // since the first call (LDPC_B200_TRACE time stamps)
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 
 static int tuning_env(const char* name) {
     const char* s = getenv(name);
@@ -428,6 +435,7 @@ extern "C" void ldpc_b200_graph_destroy(ldpc_b200_graph* g) {
     if (!g) return;
     for (auto& pl : g->placed) if (pl.worker.joinable()) pl.worker.join();
     cudaSetDevice(g->device);
+    for (auto& e : g->chunk_ev) if (e) cudaEventDestroy(e);
     cudaFree(g->d_c2v16); cudaFree(g->d_v2c16); cudaFree(g->d_work); cudaFree(g->d_raw);
     cudaFree(g->d_bec); cudaFree(g->d_out); cudaFree(g->d_stats);
     for (int i = 0; i < ldpc_b200_graph::BEC_RING; i++) { if (g->h_bec[i]) cudaFreeHost(g->h_bec[i]); if (g->h_bec_ev[i]) cudaEventDestroy(g->h_bec_ev[i]); }
@@ -718,13 +726,19 @@ static int ensure_placement(ldpc_b200_graph* g, int words, double frames, bool w
             if (place_cache_load(g, words, effort, P)) { const int rc = placement_upload(g, words, effort, P); if (rc) return rc; pl.source = 2; continue; }
         }
         graph_content_hash(g);   // computed on this thread: the worker only reads it
-        pl.search_effort = effort;
+        // Progressive: the FIRST search of a graph is a quick one (a quarter of effort 1 = 1/24 of the default's time, yet
+        // most of the gain: the natural layout costs 3.1x the conflict-free wavefront count, effort 1 1.17x, effort 6
+        // 1.11x), so that a cold run leaves the natural layout early; the next call then finds a placement of lower effort
+        // than wanted and starts the full search behind it.
+        const int search_effort = (!pl.ready && effort > 1 && tuning_env("LDPC_B200_PLACE_PROGRESSIVE") != 2) ? 1 : effort;
+        pl.search_effort = search_effort;
         pl.state.store(1);
         try {
-            pl.worker = std::thread([g, words, effort, &pl]() {
+            pl.worker = std::thread([g, words, search_effort, effort, &pl]() {
                 std::unique_ptr<Placement> R(new Placement());
-                place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, effort, 0x5EEDull, *R);
-                place_cache_store(g, words, effort, *R);
+                place_graph(g->n, g->m, g->dv, g->dc, g->v2c.data(), g->c2v.data(), 32 / words, search_effort, 0x5EEDull, *R,
+                            search_effort == 1 && search_effort != effort ? 0.25 : 1.0);
+                if (search_effort > 1) place_cache_store(g, words, search_effort, *R);   // the quick first placement is not worth a file
                 pl.result = std::move(R);
                 pl.state.store(2, std::memory_order_release);
             });
@@ -746,8 +760,8 @@ extern "C" int ldpc_b200_placement_wait(ldpc_b200_graph* g, int words, int* sour
     if (!g || words < 0 || words > 4) return fail(LDPC_B200_EINVAL, "placement_wait: bad argument");
     return guarded("placement_wait", [&] {
         CUDA_TRY(cudaSetDevice(g->device));
-        for (int w = 1; w <= 4; w++)
-            if (g->placed[w].state.load() != 0) { const int rc = ensure_placement(g, w, 0.0, true); if (rc) return rc; }
+        for (int w = 1; w <= 4; w++)   // every word width that was asked for: drive it to the full effort
+            if (g->placed[w].state.load() != 0 || g->placed[w].ready) { const int rc = ensure_placement(g, w, 0.0, true); if (rc) return rc; }
         if (source) *source = words ? (g->placed[words].ready ? g->placed[words].source : 0) : 0;
         return (int)LDPC_B200_OK;
     });
@@ -824,6 +838,7 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
     if (iterations < 0 || iterations > 65535) return fail(LDPC_B200_EINVAL, "mc_launch: iterations out of range");
     if (first_frame % 128 != 0) return fail(LDPC_B200_EINVAL, "mc_launch: first_frame must be a multiple of 128");
     cudaStream_t st = (cudaStream_t)stream;
+    if (tuning_env("LDPC_B200_TRACE")) fprintf(stderr, "[ldpc_b200] %.3f s: mc_launch enter (%llu frames/point)\n", host_seconds(), (unsigned long long)num_frames);
     CUDA_TRY(cudaSetDevice(g->device));
     if (num_frames == 0) return LDPC_B200_OK;
 
@@ -927,6 +942,7 @@ static int ldpc_b200_mc_launch_impl(ldpc_b200_graph* g, const double* eps, int n
     }
     const int slot = g->ev_count < ldpc_b200_graph::RING ? g->ev_count : -1;
     if (slot >= 0) CUDA_TRY(cudaEventRecord(g->ev0[slot], st));
+    if (tuning_env("LDPC_B200_TRACE")) fprintf(stderr, "[ldpc_b200] %.3f s: plan ready (pilot done), launching\n", host_seconds());
     int grid_used = grid;
     g->last.overlap_producers = 0;
     if (plan) {

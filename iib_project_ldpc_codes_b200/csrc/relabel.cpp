@@ -246,7 +246,7 @@ double gather_wavefronts(int n, int m, int dv, int dc, const int* v2c, const int
 }
 
 void place_graph(int n, int m, int dv, int dc, const int* v2c, const int* c2v, int B, int effort, uint64_t seed,
-                 Placement& out) {
+                 Placement& out, double budget_scale) {
     out.n = n; out.m = m; out.dv = dv; out.dc = dc; out.B = B;
     out.wavefronts_natural = gather_wavefronts(n, m, dv, dc, v2c, c2v, B);
     out.wavefronts_ideal = 0;
@@ -273,11 +273,11 @@ void place_graph(int n, int m, int dv, int dc, const int* v2c, const int* c2v, i
     }
     if (effort > 0 && n > 1 && m > 1 && threads > 1) {
         // `effort` is a time budget: every thread makes as many moves as the single-threaded search would
-        anneal_parallel(S, B, (long long)effort * 200 * ((long long)n + m), seed, threads);
+        anneal_parallel(S, B, (long long)((double)effort * 200.0 * ((double)n + m) * budget_scale), seed, threads);
         S.init_counts();   // exact tables and cost again
     } else if (effort > 0 && n > 1 && m > 1) {
         Rng rng(seed);
-        const long long moves = (long long)effort * 200 * ((long long)n + m);
+        const long long moves = (long long)((double)effort * 200.0 * ((double)n + m) * budget_scale);
         const double t0 = 0.25, t1 = 0.03;
         double T = t0;
         for (long long it = 0; it < moves && S.cost > 0; it++) {

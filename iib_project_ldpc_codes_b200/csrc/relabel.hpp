@@ -40,7 +40,8 @@ struct Placement {
 double gather_wavefronts(int n, int m, int dv, int dc, const int* v2c, const int* c2v, int B);
 
 // effort: 0 = natural layout (identity), >= 1 = optimise (annealing moves ~ effort * 200 * (n + m))
+// budget_scale multiplies the move budget (the quick first pass of the background search uses 0.25)
 void place_graph(int n, int m, int dv, int dc, const int* v2c, const int* c2v, int B, int effort, uint64_t seed,
-                 Placement& out);
+                 Placement& out, double budget_scale = 1.0);
 
 }  // namespace ldpc
