@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Time line of a cold start at BASELINE config 2 (n = 10^4, six eps points, 10^7 frames per point): first, second and third
+host-buffer call on a fresh handle with the placement cache disabled; LDPC_B200_TRACE prints which layout (natural /
+quick placement / full placement) every frame chunk was enqueued on and when."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["LDPC_B200_CACHE"] = "0"; os.environ["LDPC_B200_TRACE"] = "1"
