@@ -972,21 +972,27 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
         LDPC_FORW K[w] = valid[w];
         bool second = false;
         if (P.expurgation >= 0) {
-            for (int f = t.tid; f < W; f += t.nthr) rf[f] = 0u;
-            team_sync(t);
-            LDPC_FORW {
-                uint32_t c = 0;
-                for (int i = t.warp; i < P.n; i += t.team_warps) c += (x[i].a[w] >> t.lane) & 1u;
-                if (c) atomicAdd(&rf[w * 32 + t.lane], c);
+            // `any` already says which frames end with erasures left (residual > 0): with threshold 0 that IS the
+            // predicate, and a group without such a frame counts nothing whatever the threshold -- the per-frame
+            // residuals (a pass over the whole state, ~20 % of the ensemble kernel's instructions) are only counted
+            // for a positive threshold in a group that has a failing frame
+            uint32_t kall = 0, kany = 0, failing = 0;
+            LDPC_FORW failing |= any[w] & valid[w];
+            if (P.expurgation == 0 || failing == 0u) {
+                LDPC_FORW K[w] = any[w] & valid[w];
+            } else {
+                for (int f = t.tid; f < W; f += t.nthr) rf[f] = 0u;
+                team_sync(t);
+                LDPC_FORW {
+                    uint32_t c = 0;
+                    for (int i = t.warp; i < P.n; i += t.team_warps) c += (x[i].a[w] >> t.lane) & 1u;
+                    if (c) atomicAdd(&rf[w * 32 + t.lane], c);
+                }
+                team_sync(t);
+                LDPC_FORW K[w] = __ballot_sync(0xFFFFFFFFu, (int)rf[w * 32 + t.lane] > P.expurgation) & valid[w];
+                team_sync(t);  // rf reads done before anything reuses scratch
             }
-            team_sync(t);
-            uint32_t kall = 0, kany = 0;
-            LDPC_FORW {
-                K[w] = __ballot_sync(0xFFFFFFFFu, (int)rf[w * 32 + t.lane] > P.expurgation) & valid[w];
-                kall |= K[w] ^ valid[w];
-                kany |= K[w];
-            }
-            team_sync(t);  // rf reads done before anything reuses scratch
+            LDPC_FORW { kall |= K[w] ^ valid[w]; kany |= K[w]; }
             if (kany == 0u) {
                 // nothing counted: only the denominators move
                 if (t.tid == 0) {
