@@ -138,6 +138,18 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
     team_sync(t);
     const uint32_t nconf = conf[0];
     if (nconf > GG_MAX_CONFLICTS) return false;
+    // The swap partner of a repeat's FIRST try depends only on its rank i in the list, not on the swaps made before it:
+    // the team computes those in parallel (into the bucket array, free by now), so that the serial walk below only
+    // runs Philox for the rare second and later tries (it used to be ~10 dependent Philox calls on one thread while
+    // the rest of the team waited at the barrier).
+    uint32_t* first_try = bkt;
+    const uint32_t nfirst = min(nconf, (uint32_t)nb);
+    for (uint32_t i = t.tid; i < nfirst; i += t.nthr) {
+        uint32_t r0 = i << 16, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_REPAIR;
+        philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
+        first_try[i] = __umulhi(r0, (uint32_t)E);
+    }
+    if (nconf) team_sync(t);   // team-uniform
     // 3b. one thread: ascending order, then the swaps
     if (t.tid == 0 && nconf) {
         for (uint32_t i = 1; i < nconf; i++) {   // insertion sort
@@ -158,9 +170,13 @@ __device__ __forceinline__ bool team_generate_graph(const E1Params& P, const Gra
             for (int b = 0; b < a; b++) rep |= (at(c, b) == v);
             if (!rep) continue;   // an earlier swap already removed it
             for (uint32_t tries = 0; tries < 65536u; tries++) {
-                uint32_t r0 = (i << 16) | tries, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_REPAIR;
-                philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
-                const int s2 = (int)__umulhi(r0, (uint32_t)E);
+                int s2;
+                if (tries == 0u && i < nfirst) s2 = (int)first_try[i];
+                else {
+                    uint32_t r0 = (i << 16) | tries, r1 = g_lo, r2 = g_hi, r3 = GG_TAG_REPAIR;
+                    philox4x32_10(r0, r1, r2, r3, Gp.seed_lo, Gp.seed_hi);
+                    s2 = (int)__umulhi(r0, (uint32_t)E);
+                }
                 const int c2 = s2 / dc, j2 = s2 % dc;
                 if (c2 == c) continue;
                 const uint16_t v2 = at(c2, j2);
