@@ -880,21 +880,30 @@ __global__ void __launch_bounds__(e1_threads(WORDS), 1) e1_mc_kernel(const __gri
     }
     long long staged_graph = -1;
 
+    // Ensemble mode: a team takes ALL the frame groups of a graph (ens_gpg consecutive items), so the graph is built once
+    // per graph, not once per group (groups_per_point is a multiple of ens_gpg: a block never straddles two graphs).
+    const unsigned long long fetch = (P.ens && !P.recount && P.ens_gpg > 1) ? P.ens_gpg : 1ull;
+    unsigned long long next_item = 0, items_left = 0;
     for (;;) {
         // ---- fetch a work item (point, group) ----
         unsigned long long item;
-        if (t.team_warps == 1) {
+        if (items_left > 0) {   // team-uniform
+            item = next_item;
+        } else if (t.team_warps == 1) {
             unsigned long long v = 0;
-            if (t.lane == 0) v = atomicAdd(P.work_counter, 1ull);
+            if (t.lane == 0) v = atomicAdd(P.work_counter, fetch);
             item = __shfl_sync(0xFFFFFFFFu, v, 0);
+            items_left = fetch;
         } else {
             if (t.tid == 0) {
-                unsigned long long v = atomicAdd(P.work_counter, 1ull);
+                unsigned long long v = atomicAdd(P.work_counter, fetch);
                 work_slot[0] = (uint32_t)v; work_slot[1] = (uint32_t)(v >> 32);
             }
             team_sync(t);
             item = (unsigned long long)work_slot[0] | ((unsigned long long)work_slot[1] << 32);
+            items_left = fetch;
         }
+        next_item = item + 1; items_left--;
         if (item >= total) break;
         uint32_t point = (uint32_t)(item / P.groups_per_point);
         unsigned long long gi = item - (unsigned long long)point * P.groups_per_point;
