@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the BEC message-passing Monte-Carlo hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c4e|c5] [--scaling weak|strong]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c4e|c4e1k|c5] [--scaling weak|strong]
                     [--impl ours|reference] [--no-legs] [--no-cpu-baseline]
 
 One "step" = one pass of the fused Monte-Carlo path over one batch of synthetic input: every erasure point of the
@@ -44,6 +44,10 @@ WORKLOADS = {
                 ensemble=True, frames_per_graph=128,
                 desc="expurgated (4,8)-regular ENSEMBLE n=2000 (parallel_simulator_expurgated.py run_simulation): fresh graph "
                      "per 128 frames generated in the kernel, expurgation 0, eps 0.30-0.36, 131072 graphs per point"),
+    "c4e1k": dict(n=2000, dv=4, dc=8, eps=[0.30, 0.32, 0.34, 0.36], frames=1024 * 16384, cap=200, expurgation=0,
+                  ensemble=True, frames_per_graph=1024,
+                  desc="as c4e with a fresh graph per 1024 frames (16384 graphs per point): a team builds a graph once and decodes "
+                       "its eight 128-frame groups"),
     "c5": dict(n=4000, dv=3, dc=6, eps=[round(0.34 + 0.11 * i / 19, 6) for i in range(20)], frames=1_000_000,
                cap=200, expurgation=-1, desc="(3,6)-regular n=4000, 20 eps points 0.34-0.45, 10^6 frames per point"),
 }
