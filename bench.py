@@ -294,6 +294,7 @@ def measure_fixed(E, name, wl, steps, warmup, with_cpu, cold=True):
         step(s)
         if s == 0:
             g.wait_placement()   # the placement search runs in the background of the first step; time the placed layout
+    g.wait_placement()           # (also when there was no warm-up step at all)
     barrier()
     g.kernel_times_ms()
     g.mc_stats()
